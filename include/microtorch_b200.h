@@ -1,0 +1,213 @@
+/*
+ * microtorch_b200.h - C ABI of libmicrotorch_b200.so
+ *
+ * The drop-in boundary for MicroTorch's device="cuda" path.  The reference
+ * (nickovchinnikov/microtorch) has no FFI: its CUDA path is "substitute the cupy module
+ * for numpy" (src/tensor/device.py:74-84).  Each entry point below names the reference
+ * call site(s) (paths relative to the reference checkout) whose CuPy work it replaces.
+ * Plain pointers and sizes only; no torch, no C++ types.
+ *
+ * Conventions
+ *   - every function returns 0 (MT_OK) or a non-zero mt_status; the message for the last
+ *     failure on the calling thread is mt_last_error().
+ *   - all device pointers come from mt_malloc (caching pool); all arithmetic is float32
+ *     ("everything is fp32").
+ *   - one compute stream per process (one process per GPU); calls are asynchronous with
+ *     respect to the host unless stated (mt_d2h, mt_sync, mt_event_sync block).
+ *   - shapes/strides arrays are read during the call only; strides are in ELEMENTS and a
+ *     stride of 0 broadcasts that dimension.
+ *   - there is no CPU fallback: without a usable B200 every compute entry point fails.
+ */
+#ifndef MICROTORCH_B200_H
+#define MICROTORCH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MT_MAX_DIMS 8
+
+typedef enum mt_status {
+  MT_OK = 0,
+  MT_ERR_CUDA = 1,        /* a CUDA runtime/driver call failed */
+  MT_ERR_INVALID = 2,     /* bad argument (shape, alignment, enum) */
+  MT_ERR_NOT_INIT = 3,    /* mt_init has not succeeded in this process */
+  MT_ERR_OOM = 4,         /* device allocation failed even after trimming the pool */
+  MT_ERR_NCCL = 5,        /* NCCL missing or a collective failed */
+  MT_ERR_UNSUPPORTED = 6  /* valid request this library does not implement */
+} mt_status;
+
+/* ---------------------------------------------------------------- runtime --------- */
+/* replaces: CUDA_AVAILABLE = cp.cuda.is_available()  (src/tensor/device.py:7-11)      */
+int mt_device_count(int* count);
+/* replaces: CuPy's implicit context/stream creation on first use (device.py:74-84)    */
+int mt_init(int device);
+int mt_shutdown(void);
+int mt_is_initialized(void);
+const char* mt_last_error(void);
+const char* mt_version(void);
+int mt_device_info(char* name, size_t name_cap, int* sm_count, size_t* hbm_bytes,
+                   int* cc_major, int* cc_minor);
+/* replaces: the implicit device sync at .item()/.get()/print (src/tensor/tensor.py:175-183) */
+int mt_sync(void);
+/* the library's compute stream as a cudaStream_t (for interop/timing only)             */
+int mt_stream(void** cuda_stream);
+/* CUDA events on the compute stream (bench timing; demo.ipynb:5176,5194 uses time.time) */
+int mt_event_create(void** ev);
+int mt_event_record(void* ev);
+int mt_event_sync(void* ev);
+int mt_event_elapsed_ms(void* start, void* stop, float* ms);
+int mt_event_destroy(void* ev);
+/* number of kernels this library has launched since the last reset (bench "gpu_launches") */
+int mt_launch_count(uint64_t* count);
+int mt_launch_count_reset(void);
+/* overwrite a buffer larger than L2 (timing hygiene between timed iterations)           */
+int mt_l2_flush(void);
+
+/* ---------------------------------------------------------------- memory ---------- */
+/* replaces: CuPy's default MemoryPool behind every cp.array / zeros_like / operator
+ * result (src/tensor/tensor.py:77,205,243; every op in src/tensor/ops/)                  */
+int mt_malloc(void** ptr, size_t bytes);
+int mt_free(void* ptr);
+int mt_pool_stats(size_t* reserved_bytes, size_t* in_use_bytes, size_t* peak_in_use_bytes,
+                  uint64_t* n_requests, uint64_t* n_device_mallocs);
+int mt_pool_trim(void);
+/* pinned host staging (end-to-end path: H2D of a step's inputs, D2H of its loss)        */
+int mt_host_alloc(void** ptr, size_t bytes);
+int mt_host_free(void* ptr);
+/* replaces: cp.array(np_array) (tensor.py:205,221) / .get() (tensor.py:218)             */
+int mt_h2d(void* dst, const void* src, size_t bytes);        /* blocks until src is reusable */
+int mt_d2h(void* dst, const void* src, size_t bytes);        /* blocks until dst is valid    */
+int mt_h2d_async(void* dst, const void* pinned_src, size_t bytes);
+int mt_d2h_async(void* pinned_dst, const void* src, size_t bytes);
+int mt_d2d(void* dst, const void* src, size_t bytes);
+/* replaces: zeros_like + grad.fill(0.0) (tensor.py:77-85,243-248; module.py:83-89)      */
+int mt_memset_zero(void* ptr, size_t bytes);
+int mt_memset_multi(void* const* ptrs, const size_t* bytes, int count);
+int mt_fill_f32(float* out, size_t n, float value);
+/* replaces: implicit strided reads of transposed/sliced/broadcast views - .copy(),
+ * .get() of a view, np.broadcast_to materialisation (base.py:63,111; tensor.py:380)     */
+int mt_copy_strided_f32(float* out, const float* in, int ndim, const int64_t* shape,
+                        const int64_t* in_strides);
+/* replaces: full_grad[index] = grad for basic (slice) indices (overload.py:36-38)       */
+int mt_scatter_strided_f32(float* out, const int64_t* out_strides, const float* in, int ndim,
+                           const int64_t* shape);
+/* replaces: tensor.data[index] / full_grad[index] = grad with an integer index array
+ * on axis 0 (overload.py:28,37).  Rows are `row_elems` contiguous floats; the scatter
+ * ASSIGNS (last writer wins is avoided: duplicates resolve to the highest position,
+ * as NumPy does).                                                                        */
+int mt_gather_rows_f32(float* out, const float* in, const int64_t* dev_index, int64_t n_index,
+                       int64_t row_elems, int64_t n_rows);
+int mt_scatter_rows_assign_f32(float* out, const float* in, const int64_t* dev_index,
+                               int64_t n_index, int64_t row_elems, int64_t n_rows);
+
+/* ---------------------------------------------------------------- elementwise ----- */
+typedef enum mt_binary_op {
+  MT_BIN_ADD = 0,       /* a + b            overload.py:70;  tensor.py:279 (grad accumulate)   */
+  MT_BIN_MUL = 1,       /* a * b            overload.py:94,109                                 */
+  MT_BIN_SUB = 2,       /* a - b            (a + (-b), tensor.py:556-558, fused)               */
+  MT_BIN_DIV = 3,       /* a / b            math.py:12 (log backward g / x)                    */
+  MT_BIN_TANH_BWD = 4,  /* a * (1 - b*b)    math.py:74   a = grad, b = saved tanh OUTPUT       */
+  MT_BIN_POW_BWD = 5,   /* a * (p * b**(p-1))  math.py:51   a = grad, b = saved input, p = scalar */
+  MT_BIN_EXP_BWD = 6    /* a * b            math.py:31   a = grad, b = saved exp output        */
+} mt_binary_op;
+
+/* out[idx] = op(a[idx . a_strides], b[idx . b_strides]) over the broadcast `shape`;
+ * out is contiguous.  Vectorised (128-bit) whenever the collapsed layout allows it.     */
+int mt_ew_binary_f32(int op, float* out, const float* a, const float* b, int ndim,
+                     const int64_t* shape, const int64_t* a_strides, const int64_t* b_strides,
+                     float scalar);
+/* in-place broadcasting update  dst[idx] (+=|*=|/=) src[idx . src_strides]
+ * replaces: np.add/multiply/true_divide(self.data, other, out=self.data)
+ * (tensor.py:547-550 bias add, :581-588, :609-616).  dst may itself be strided.         */
+int mt_ew_inplace_f32(int op, float* dst, const int64_t* dst_strides, const float* src,
+                      const int64_t* src_strides, int ndim, const int64_t* shape);
+
+typedef enum mt_unary_op {
+  MT_UN_NEG = 0,        /* -x          overload.py:52               */
+  MT_UN_LOG = 1,        /* log x       math.py:8                    */
+  MT_UN_TANH = 2,       /* tanh x      math.py:70                   */
+  MT_UN_EXP = 3,        /* exp x       math.py:27                   */
+  MT_UN_POW = 4,        /* x ** s      math.py:47 (NumPy fast paths for s in {-1,0,0.5,1,2}) */
+  MT_UN_SCALE = 5,      /* x * s       optimizer.py:39 (lr * grad); tensor.py:310            */
+  MT_UN_ADDS = 6        /* x + s                                                            */
+} mt_unary_op;
+int mt_ew_unary_f32(int op, float* out, const float* x, size_t n, float scalar);
+
+/* ---------------------------------------------------------------- reductions ------ */
+/* x viewed as [outer, red, inner] (contiguous); out[o,i] = sum_r x[o,r,i] * w[o,r,i]
+ * where w is `other` addressed with strides (so, sr, si) or 1 when other == NULL.
+ * Deterministic (fixed tree, no float atomics).
+ * replaces: tlib.sum(x, axis, keepdims) (reduce.py:11); grad.sum(), grad.sum(axis=...)
+ * in BaseOps.bkwd_broadcast (base.py:28-54) and, with `other`, the `grad * b.data`
+ * that precedes it in mul backward (overload.py:109-112).                               */
+int mt_reduce_sum_f32(float* out, const float* x, int64_t outer, int64_t red, int64_t inner,
+                      const float* other, int64_t other_so, int64_t other_sr, int64_t other_si);
+
+/* ---------------------------------------------------------------- Linear / matmul -- */
+typedef enum mt_act { MT_ACT_NONE = 0, MT_ACT_TANH = 1 } mt_act;
+
+/* Y[M,N] = act( X[M,K] . W[N,K]^T + bias[N] )      X, W, Y row-major, contiguous
+ * replaces: Linear.forward = (W @ x^T)^T, `output += bias` and the following Tanh
+ * (src/nn/layer/linear.py:48-62, src/nn/activation.py:11-12, overload.py:132).
+ * tcgen05/TMEM 3xTF32 tiles fed by TMA; bias add + tanh fused in the epilogue.          */
+int mt_linear_fwd_f32(float* Y, const float* X, const float* W, const float* bias_or_null,
+                      int64_t M, int64_t N, int64_t K, int act);
+/* dZ = dY * (1 - Yact^2) if Yact != NULL else dY          (tanh' fused in the prologue)
+ * dW[N,K] (+)= dZ^T . X ;  dX[M,K] = dZ . W   (dX skipped when NULL).  No bias gradient:
+ * the reference's bias is outside the tape (linear.py:61-62, tensor.py:547-550; Q1).
+ * replaces: matmul.bkwd_a / bkwd_b (overload.py:137-154) and tanh backward (math.py:74) */
+int mt_linear_bwd_f32(float* dX_or_null, float* dW, const float* dY, const float* Yact_or_null,
+                      const float* X, const float* W, int64_t M, int64_t N, int64_t K,
+                      int accumulate_dW);
+/* generic C[b] = A[b] @ B[b] for the bare `@` (overload.py:132,142,153): element strides
+ * for every operand, batch stride 0 broadcasts.  C is row-major [batch, M, N].          */
+int mt_matmul_f32(float* C, const float* A, const float* B, int64_t batch, int64_t M, int64_t N,
+                  int64_t K, int64_t a_sb, int64_t a_sm, int64_t a_sk, int64_t b_sb, int64_t b_sk,
+                  int64_t b_sn);
+/* which GEMM engine the last mt_linear_ / mt_matmul_ call used: 1 = tcgen05, 0 = SIMT fp32 */
+int mt_gemm_last_engine(int* engine);
+/* force the engine: -1 auto (default), 0 SIMT only, 1 tcgen05 only (error if the shape
+ * is not supported by it).  Test/diagnostic hook.                                       */
+int mt_gemm_set_engine(int engine);
+
+/* ---------------------------------------------------------------- losses ---------- */
+typedef enum mt_loss_kind {
+  MT_LOSS_MSE = 0,      /* mean((p - t)^2)                          src/nn/loss.py:63-76  */
+  MT_LOSS_CE_REF = 1,   /* mean(log p - t)  [the reference's formula] src/nn/loss.py:79-84 */
+  MT_LOSS_BCE = 2       /* mean(-(t log p + (1-t) log(1-p)))        src/nn/loss.py:87-100 */
+} mt_loss_kind;
+/* loss_out[0] = scale * sum_i f(pred_i, target_i);  dpred_i = scale * f'(pred_i, target_i)
+ * (dpred skipped when NULL).  One pass: read p, read t, write dp.
+ * replaces: the 6/7/13-node expression graphs of loss.py + Reduce.mean (reduce.py:40-43)
+ * and their backward chains.  `scale` is float32(1/N) of the GLOBAL element count.      */
+int mt_loss_fwd_bwd_f32(int kind, float* loss_out, float* dpred_or_null, const float* pred,
+                        const float* target, size_t n, float scale);
+
+/* ---------------------------------------------------------------- optimizer ------- */
+/* p_i -= lr * g_i for every tensor in one launch; optionally zero g_i in the same pass.
+ * replaces: SGD.step (src/nn/optimizer.py:37-39 -> tensor.py:564-571: 3 kernels + 2
+ * temporaries per Parameter) and the following Module.zero_grad (module.py:83-89).      */
+int mt_sgd_multi_f32(float* const* params, float* const* grads, const size_t* sizes, int count,
+                     float lr, int zero_grads);
+
+/* ---------------------------------------------------------------- collective ------ */
+/* Data-parallel gradient exchange (no counterpart in the reference: new component,
+ * SURVEY.md section 8(e)).  NCCL is dlopen()ed from `libnccl_path` (NULL = "libnccl.so.2"). */
+int mt_comm_load(const char* libnccl_path);
+int mt_comm_unique_id(char* out_bytes_128);
+int mt_comm_init_rank(const char* id_bytes_128, int rank, int world);
+int mt_comm_world(int* rank, int* world);
+/* sum-allreduce `n` floats in place on the communication stream; ordered after all work
+ * already queued on the compute stream.  mt_comm_wait() makes the compute stream wait.  */
+int mt_allreduce_sum_f32(float* buf, size_t n);
+int mt_comm_wait(void);
+int mt_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICROTORCH_B200_H */

@@ -1,0 +1,154 @@
+"""ctypes binding of libmicrotorch_b200.so (the C ABI declared in include/microtorch_b200.h).
+
+This is the ONLY place the shared library is touched.  There is no fallback: if the library
+is missing, cannot be loaded, or no B200 is visible, `lib()` / `require_device()` raise - the
+CUDA path never silently runs somewhere else.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+from . import _build
+
+_LIB: Optional[C.CDLL] = None
+_DEVICE_READY = False
+
+c_f32p = C.POINTER(C.c_float)
+c_i64p = C.POINTER(C.c_int64)
+c_sizep = C.POINTER(C.c_size_t)
+c_u64p = C.POINTER(C.c_uint64)
+c_voidpp = C.POINTER(C.c_void_p)
+VP = C.c_void_p
+
+# name -> (argtypes, doc)   every symbol include/microtorch_b200.h declares
+PROTOTYPES = {
+    "mt_device_count": [C.POINTER(C.c_int)],
+    "mt_init": [C.c_int],
+    "mt_shutdown": [],
+    "mt_is_initialized": [],
+    "mt_device_info": [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), c_sizep, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "mt_sync": [],
+    "mt_stream": [c_voidpp],
+    "mt_event_create": [c_voidpp],
+    "mt_event_record": [VP],
+    "mt_event_sync": [VP],
+    "mt_event_elapsed_ms": [VP, VP, C.POINTER(C.c_float)],
+    "mt_event_destroy": [VP],
+    "mt_launch_count": [c_u64p],
+    "mt_launch_count_reset": [],
+    "mt_l2_flush": [],
+    "mt_malloc": [c_voidpp, C.c_size_t],
+    "mt_free": [VP],
+    "mt_pool_stats": [c_sizep, c_sizep, c_sizep, c_u64p, c_u64p],
+    "mt_pool_trim": [],
+    "mt_host_alloc": [c_voidpp, C.c_size_t],
+    "mt_host_free": [VP],
+    "mt_h2d": [VP, VP, C.c_size_t],
+    "mt_d2h": [VP, VP, C.c_size_t],
+    "mt_h2d_async": [VP, VP, C.c_size_t],
+    "mt_d2h_async": [VP, VP, C.c_size_t],
+    "mt_d2d": [VP, VP, C.c_size_t],
+    "mt_memset_zero": [VP, C.c_size_t],
+    "mt_memset_multi": [c_voidpp, c_sizep, C.c_int],
+    "mt_fill_f32": [VP, C.c_size_t, C.c_float],
+    "mt_copy_strided_f32": [VP, VP, C.c_int, c_i64p, c_i64p],
+    "mt_scatter_strided_f32": [VP, c_i64p, VP, C.c_int, c_i64p],
+    "mt_gather_rows_f32": [VP, VP, VP, C.c_int64, C.c_int64, C.c_int64],
+    "mt_scatter_rows_assign_f32": [VP, VP, VP, C.c_int64, C.c_int64, C.c_int64],
+    "mt_ew_binary_f32": [C.c_int, VP, VP, VP, C.c_int, c_i64p, c_i64p, c_i64p, C.c_float],
+    "mt_ew_inplace_f32": [C.c_int, VP, c_i64p, VP, c_i64p, C.c_int, c_i64p],
+    "mt_ew_unary_f32": [C.c_int, VP, VP, C.c_size_t, C.c_float],
+    "mt_reduce_sum_f32": [VP, VP, C.c_int64, C.c_int64, C.c_int64, VP, C.c_int64, C.c_int64, C.c_int64],
+    "mt_linear_fwd_f32": [VP, VP, VP, VP, C.c_int64, C.c_int64, C.c_int64, C.c_int],
+    "mt_linear_bwd_f32": [VP, VP, VP, VP, VP, VP, C.c_int64, C.c_int64, C.c_int64, C.c_int],
+    "mt_matmul_f32": [VP, VP, VP] + [C.c_int64] * 10,
+    "mt_gemm_last_engine": [C.POINTER(C.c_int)],
+    "mt_gemm_set_engine": [C.c_int],
+    "mt_loss_fwd_bwd_f32": [C.c_int, VP, VP, VP, VP, C.c_size_t, C.c_float],
+    "mt_sgd_multi_f32": [c_voidpp, c_voidpp, c_sizep, C.c_int, C.c_float, C.c_int],
+    "mt_comm_load": [C.c_char_p],
+    "mt_comm_unique_id": [C.c_char_p],
+    "mt_comm_init_rank": [C.c_char_p, C.c_int, C.c_int],
+    "mt_comm_world": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "mt_allreduce_sum_f32": [VP, C.c_size_t],
+    "mt_comm_wait": [],
+    "mt_comm_destroy": [],
+}
+# return `const char*`
+STRING_FUNCS = ("mt_last_error", "mt_version")
+
+# enums of the header
+BIN_ADD, BIN_MUL, BIN_SUB, BIN_DIV, BIN_TANH_BWD, BIN_POW_BWD, BIN_EXP_BWD = range(7)
+UN_NEG, UN_LOG, UN_TANH, UN_EXP, UN_POW, UN_SCALE, UN_ADDS = range(7)
+ACT_NONE, ACT_TANH = 0, 1
+LOSS_MSE, LOSS_CE_REF, LOSS_BCE = 0, 1, 2
+
+
+class MicrotorchB200Error(RuntimeError):
+    """A C-ABI call returned a non-zero mt_status."""
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """dlopen the shared library and declare every prototype.  Raises if it is absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = path or os.environ.get("MICROTORCH_B200_LIB") or _build.lib_path()
+    if not os.path.exists(path):
+        raise MicrotorchB200Error(
+            f"{path} not found: build it with `python -m microtorch_b200._build` "
+            "(there is no CPU fallback for device='cuda')")
+    lib = C.CDLL(path)
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    for name in STRING_FUNCS:
+        fn = getattr(lib, name)
+        fn.argtypes = []
+        fn.restype = C.c_char_p
+    _LIB = lib
+    return lib
+
+
+def lib() -> C.CDLL:
+    return _LIB if _LIB is not None else load_library()
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().mt_last_error().decode(errors="replace")
+        raise MicrotorchB200Error(f"{what or 'libmicrotorch_b200'} failed (status {status}): {msg}")
+
+
+def device_count() -> int:
+    """Number of visible CUDA devices; 0 when there is no driver/GPU (never raises for that)."""
+    try:
+        n = C.c_int(0)
+        if lib().mt_device_count(C.byref(n)) != 0:
+            return 0
+        return n.value
+    except (MicrotorchB200Error, OSError):
+        return 0
+
+
+def require_device(device: Optional[int] = None) -> None:
+    """Initialise the library on this process's GPU (LOCAL_RANK by default)."""
+    global _DEVICE_READY
+    if _DEVICE_READY:
+        return
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    check(lib().mt_init(device), "mt_init")
+    _DEVICE_READY = True
+
+
+def device_ready() -> bool:
+    return _DEVICE_READY
+
+
+def i64(values: Sequence[int]):
+    return (C.c_int64 * max(len(values), 1))(*values)

@@ -1,0 +1,32 @@
+// mt_gemm.cuh - shared argument block of the two GEMM engines (tcgen05 and SIMT).
+#pragma once
+#include "mt_common.cuh"
+
+namespace mt {
+
+// C[m,n] (+)= act( sum_k A'(m,k) * B(k,n) + bias[n] ),  C row-major [M,N] (ld = N)
+//   A(m,k)  = A[m*a_sm + k*a_sk]            (+ b*a_sb for the batched SIMT path)
+//   B(k,n)  = B[k*b_sk + n*b_sn]
+//   A'(m,k) = A(m,k) * (1 - T(m,k)^2) when `tanh_src` != NULL, T addressed like A
+//             (tanh' fused into the operand prologue; tcgen05 engine only)
+struct GemmArgs {
+  float* C;
+  const float* A;
+  const float* B;
+  long long M, N, K;
+  long long a_sb, a_sm, a_sk, b_sb, b_sk, b_sn;
+  const float* bias;      // [N] or NULL
+  const float* tanh_src;  // same layout as A, or NULL
+  int act;                // mt_act
+  int accumulate;         // C += result
+  // SIMT split-K bookkeeping (filled by gemm_simt)
+  int splits;
+  long long kchunk;
+};
+
+int gemm_simt(GemmArgs a, long long batch);
+// MT_OK if the tcgen05 engine ran it, MT_ERR_UNSUPPORTED if the layout/shape is not one it
+// takes (caller falls back to SIMT), anything else is a real error.
+int gemm_tc_try(const GemmArgs& a);
+
+}  // namespace mt

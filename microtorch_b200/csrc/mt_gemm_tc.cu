@@ -1,0 +1,537 @@
+// mt_gemm_tc.cu - fp32-accurate GEMM on the Blackwell tensor cores (tcgen05 + TMEM + TMA), 3xTF32.
+//
+// Replaces cuBLAS SGEMM behind the reference's `a.data @ b.data`, `grad @ b.T`, `a.T @ grad`
+// (src/tensor/ops/overload.py:132,142,153) as used by Linear (src/nn/layer/linear.py:48).
+//
+//   C[M,N] (+)= act( A'[M,K] . B[K,N] + bias[N] )          fp32 in, fp32 out
+//
+// 3xTF32 split done ON CHIP: x = hi + lo with hi = tf32(x), lo = tf32(x - hi);
+//   A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi   (lo.lo ~ 2^-22 is dropped), fp32 accumulate in TMEM.
+// No split copies ever touch HBM: TMA lands the raw fp32 tile in shared memory, four
+// "converter" warps rewrite it in place as hi and write lo to a twin buffer with the SAME
+// (swizzled) layout - the conversion is element-wise on the byte image, so it is independent of
+// the swizzle - then hand the stage to the single MMA-issuing thread.  The backward prologue
+// dZ = dY * (1 - Y^2) is fused into the same pass (the Y tile is TMA-loaded into the lo buffer).
+//
+// CTA = 10 warps, persistent over output tiles (grid = #SMs), 128 x BN x 32 tiles:
+//   warp 0      TMA producer      (one lane)            full[s]  <- bytes landed
+//   warps 2-5   converters        (128 threads)         conv[s]  <- hi/lo ready (generic->async proxy fence)
+//   warp 1      MMA issuer        (one lane) + TMEM     empty[s] <- tcgen05.commit, tfull[a] <- tile done
+//   warps 6-9   epilogue          (128 threads)         tempty[a] <- accumulator drained
+// Two TMEM accumulators (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Operands may be K-major or MN-major (UMMA descriptor transpose bits), so forward (X.W^T), dX
+// (dZ.W) and dW (dZ^T.X) all read the row-major activations/weights in place - no transposes.
+//
+// Roofline: tensor pipe.  One k-block (32) of a 128x256 tile is 12 tcgen05.mma (M128 N256 K8),
+// 128 cycles each; the logical 2*M*N*K flops are reported against (TF32 dense peak)/3.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "mt_common.cuh"
+#include "mt_gemm.cuh"
+
+using namespace mt;
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;            // 32 fp32 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;         // kind::tf32: 32 B of K per instruction
+constexpr int NUM_THREADS = 320;
+constexpr int NUM_ACC = 2;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must end in a trap (a clean CUDA error), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("mt_gemm_tc: mbarrier wait timed out (role %d, block %d, thread %d, parity %u)\n", who, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor (SM100 format, version 1), SWIZZLE_128B.
+//   K-major : rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused (encoded 1).
+//   MN-major: 32-element (128 B) MN atoms 4096 B apart (LBO = one 32x32 TMA box), k-groups of 8 at SBO = 1024 B.
+__host__ __device__ constexpr uint64_t make_smem_desc_base(bool mn_major) {
+  return (uint64_t(mn_major ? (4096 >> 4) : 1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+__device__ __forceinline__ uint64_t smem_desc(uint64_t base, uint32_t addr) {
+  return base | uint64_t((addr & 0x3FFFFu) >> 4);
+}
+// Instruction descriptor: D=f32, A=B=tf32, majors, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) |
+         (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+struct Params {
+  float* C;
+  const float* bias;
+  long long M, N, K;
+  int act, accumulate;
+  int m_blocks, n_blocks, k_blocks;
+  int has_prologue;   // A' = A * (1 - T^2)
+  int write_hi;       // converters store hi explicitly (else rely on the MMA ignoring the low 13 bits)
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_TILE = BM * BK * 4;
+  static constexpr int B_TILE = BN * BK * 4;
+  static constexpr int STAGE = 2 * (A_TILE + B_TILE);   // raw + lo twins
+  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = (NUM_ACC * BN <= 256) ? 256 : 512;
+};
+
+// hi/lo split of one 16-byte vector.  RN=true rounds hi to nearest tf32 (needs the explicit hi store).
+template <bool RN>
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  const uint32_t add = RN ? 0x1000u : 0u;
+  hi.x = __uint_as_float((__float_as_uint(v.x) + add) & 0xFFFFE000u);
+  hi.y = __uint_as_float((__float_as_uint(v.y) + add) & 0xFFFFE000u);
+  hi.z = __uint_as_float((__float_as_uint(v.z) + add) & 0xFFFFE000u);
+  hi.w = __uint_as_float((__float_as_uint(v.w) + add) & 0xFFFFE000u);
+  lo.x = __uint_as_float((__float_as_uint(v.x - hi.x) + 0x1000u) & 0xFFFFE000u);
+  lo.y = __uint_as_float((__float_as_uint(v.y - hi.y) + 0x1000u) & 0xFFFFE000u);
+  lo.z = __uint_as_float((__float_as_uint(v.z - hi.z) + 0x1000u) & 0xFFFFE000u);
+  lo.w = __uint_as_float((__float_as_uint(v.w - hi.w) + 0x1000u) & 0xFFFFE000u);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ CUtensorMap map_t, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // barrier block after the stages
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto conv_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * C::STAGES + NUM_ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * C::STAGES + 2 * NUM_ACC);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE + 8 * (3 * C::STAGES + 2 * NUM_ACC));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    if (p.has_prologue) prefetch_tmap(&map_t);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), 4);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < NUM_ACC; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int num_tiles = p.m_blocks * p.n_blocks;
+  const int kb_count = p.k_blocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = C::A_TILE + C::B_TILE + (p.has_prologue ? C::A_TILE : 0);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+        for (int kb = 0; kb < kb_count; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1, 0);
+          const uint32_t sa = smem_base + stage * C::STAGE;
+          const uint32_t sb = sa + C::A_TILE;
+          const uint32_t sa_lo = sb + C::B_TILE;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, tx_bytes);
+          const int k0 = kb * BK;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j) {   // 32(m) x 32(k) boxes, 4096 B each
+              tma_load_2d(sa + j * 4096, &map_a, fb, m0 + j * 32, k0);
+              if (p.has_prologue) tma_load_2d(sa_lo + j * 4096, &map_t, fb, m0 + j * 32, k0);
+            }
+          } else {
+            tma_load_2d(sa, &map_a, fb, k0, m0);    // 32(k) x 128(m) box
+            if (p.has_prologue) tma_load_2d(sa_lo, &map_t, fb, k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, fb, n0 + j * 32, k0);
+          } else {
+            tma_load_2d(sb, &map_b, fb, k0, n0);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+      constexpr uint64_t adesc_base = make_smem_desc_base(A_MN);
+      constexpr uint64_t bdesc_base = make_smem_desc_base(B_MN);
+      constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;   // bytes per UMMA_K slice
+      constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1, 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kb_count; ++kb) {
+          mbar_wait(conv_bar(stage), phase, 2);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE;
+          const uint32_t sb = sa + C::A_TILE;
+          const uint32_t sa_lo = sb + C::B_TILE;
+          const uint32_t sb_lo = sa_lo + C::A_TILE;
+#pragma unroll
+          for (int j = 0; j < BK / UMMA_K; ++j) {
+            const uint64_t a_hi = smem_desc(adesc_base, sa + j * a_kstep);
+            const uint64_t a_lo = smem_desc(adesc_base, sa_lo + j * a_kstep);
+            const uint64_t b_hi = smem_desc(bdesc_base, sb + j * b_kstep);
+            const uint64_t b_lo = smem_desc(bdesc_base, sb_lo + j * b_kstep);
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb | j) != 0);   // small terms first
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));                 // stage reusable once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));                     // accumulator complete
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== converters (128 threads) =====================
+    const int ct = threadIdx.x - 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kb_count; ++kb) {
+        mbar_wait(full_bar(stage), phase, 3);
+        uint8_t* sa = smem_gen + stage * C::STAGE;
+        uint8_t* sb = sa + C::A_TILE;
+        uint8_t* sa_lo = sb + C::B_TILE;
+        uint8_t* sb_lo = sa_lo + C::A_TILE;
+        if (p.has_prologue) {
+#pragma unroll 4
+          for (int i = ct; i < C::A_TILE / 16; i += 128) {
+            const float4 g = reinterpret_cast<float4*>(sa)[i];
+            const float4 y = reinterpret_cast<float4*>(sa_lo)[i];
+            float4 z, hi, lo;
+            z.x = __fmul_rn(g.x, __fsub_rn(1.f, __fmul_rn(y.x, y.x)));
+            z.y = __fmul_rn(g.y, __fsub_rn(1.f, __fmul_rn(y.y, y.y)));
+            z.z = __fmul_rn(g.z, __fsub_rn(1.f, __fmul_rn(y.z, y.z)));
+            z.w = __fmul_rn(g.w, __fsub_rn(1.f, __fmul_rn(y.w, y.w)));
+            split4<true>(z, hi, lo);
+            reinterpret_cast<float4*>(sa)[i] = hi;
+            reinterpret_cast<float4*>(sa_lo)[i] = lo;
+          }
+        } else if (p.write_hi) {
+#pragma unroll 4
+          for (int i = ct; i < C::A_TILE / 16; i += 128) {
+            float4 hi, lo;
+            split4<true>(reinterpret_cast<float4*>(sa)[i], hi, lo);
+            reinterpret_cast<float4*>(sa)[i] = hi;
+            reinterpret_cast<float4*>(sa_lo)[i] = lo;
+          }
+        } else {
+#pragma unroll 4
+          for (int i = ct; i < C::A_TILE / 16; i += 128) {
+            float4 hi, lo;
+            split4<false>(reinterpret_cast<float4*>(sa)[i], hi, lo);
+            reinterpret_cast<float4*>(sa_lo)[i] = lo;
+          }
+        }
+        if (p.write_hi) {
+#pragma unroll 4
+          for (int i = ct; i < C::B_TILE / 16; i += 128) {
+            float4 hi, lo;
+            split4<true>(reinterpret_cast<float4*>(sb)[i], hi, lo);
+            reinterpret_cast<float4*>(sb)[i] = hi;
+            reinterpret_cast<float4*>(sb_lo)[i] = lo;
+          }
+        } else {
+#pragma unroll 4
+          for (int i = ct; i < C::B_TILE / 16; i += 128) {
+            float4 hi, lo;
+            split4<false>(reinterpret_cast<float4*>(sb)[i], hi, lo);
+            reinterpret_cast<float4*>(sb_lo)[i] = lo;
+          }
+        }
+        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar(stage));
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 6..9 -> TMEM lane quadrants 2,3,0,1) =====================
+    const int quad = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const long long m0 = (long long)(tile / p.n_blocks) * BM, n0 = (long long)(tile % p.n_blocks) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase, 4);
+      tc_fence_after();
+      const long long row = m0 + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+      float* crow = p.C + row * p.N;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {           // accumulator fully read: give it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        const long long nb = n0 + c * 32;
+        if (row < p.M && nb < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (nb + j < p.N) {           // N % 4 == 0 (checked on the host)
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                     __uint_as_float(r[j + 3]));
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (p.act == MT_ACT_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+              float4* dst = reinterpret_cast<float4*>(crow + nb + j);
+              if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+              *dst = v;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: dim0 = contiguous extent `inner`, dim1 = `outer` rows `ld` elements apart.
+static int make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_inner,
+                    int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(MT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%dx%d", (int)r,
+                inner, outer, ld, box_inner, box_outer);
+  return MT_OK;
+}
+
+static int g_write_hi = 1;   // safe default until the hardware's tf32 operand rounding is pinned
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const GemmArgs& a, long long lda, long long ldb) {
+  using C = Cfg<BN>;
+  CUtensorMap ma, mb, mt;
+  int rc;
+  if (A_MN) rc = make_map(&ma, a.A, a.M, a.K, lda, 32, BK);
+  else rc = make_map(&ma, a.A, a.K, a.M, lda, BK, BM);
+  if (rc) return rc;
+  if (B_MN) rc = make_map(&mb, a.B, a.N, a.K, ldb, 32, BK);
+  else rc = make_map(&mb, a.B, a.K, a.N, ldb, BK, BN);
+  if (rc) return rc;
+  if (a.tanh_src) {
+    if (A_MN) rc = make_map(&mt, a.tanh_src, a.M, a.K, lda, 32, BK);
+    else rc = make_map(&mt, a.tanh_src, a.K, a.M, lda, BK, BM);
+    if (rc) return rc;
+  } else {
+    mt = ma;
+  }
+  Params p;
+  p.C = a.C;
+  p.bias = a.bias;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.act = a.act;
+  p.accumulate = a.accumulate;
+  p.m_blocks = (int)ceil_div(a.M, BM);
+  p.n_blocks = (int)ceil_div(a.N, BN);
+  p.k_blocks = (int)ceil_div(a.K, BK);
+  p.has_prologue = a.tanh_src ? 1 : 0;
+  p.write_hi = g_write_hi;
+  auto kern = gemm3xtf32_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  const long long tiles = (long long)p.m_blocks * p.n_blocks;
+  const int grid = (int)std::min<long long>(tiles, g().sm_count);
+  kern<<<grid, NUM_THREADS, C::SMEM, g().stream>>>(ma, mb, mt, p);
+  MT_LAUNCHED();
+  return MT_OK;
+}
+
+template <int BN>
+static int dispatch_major(const GemmArgs& a, bool a_mn, bool b_mn, long long lda, long long ldb) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(a, lda, ldb);
+  if (!a_mn && b_mn) return launch<BN, false, true>(a, lda, ldb);
+  if (a_mn && !b_mn) return launch<BN, true, false>(a, lda, ldb);
+  return launch<BN, true, true>(a, lda, ldb);
+}
+
+}  // namespace tc
+
+namespace mt {
+
+int gemm_tc_try(const GemmArgs& a) {
+  // operand classification
+  bool a_mn, b_mn;
+  long long lda, ldb;
+  if (a.a_sk == 1 && a.a_sm >= a.K) { a_mn = false; lda = a.a_sm; }
+  else if (a.a_sm == 1 && a.a_sk >= a.M) { a_mn = true; lda = a.a_sk; }
+  else return MT_ERR_UNSUPPORTED;
+  if (a.b_sk == 1 && a.b_sn >= a.K) { b_mn = false; ldb = a.b_sn; }
+  else if (a.b_sn == 1 && a.b_sk >= a.N) { b_mn = true; ldb = a.b_sk; }
+  else return MT_ERR_UNSUPPORTED;
+  // TMA: 16 B aligned bases and row pitches; epilogue: float4 rows of C / bias
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(a.A) || !al16(a.B) || !al16(a.C) || (a.bias && !al16(a.bias)) || (a.tanh_src && !al16(a.tanh_src)))
+    return MT_ERR_UNSUPPORTED;
+  if (lda % 4 || ldb % 4 || a.N % 4) return MT_ERR_UNSUPPORTED;
+  // worthwhile shapes only: small / skinny problems are SIMT territory (HBM- or latency-bound)
+  if (g().gemm_engine_force != 1) {
+    if (a.M < 128 || a.N < 64 || a.K < 32) return MT_ERR_UNSUPPORTED;
+  } else if (a.M < 1 || a.N < 4 || a.K < 1) {
+    return MT_ERR_UNSUPPORTED;
+  }
+  if (ceil_div(a.M, tc::BM) * ceil_div(a.N, 128) > 0x7fffffffLL) return MT_ERR_UNSUPPORTED;
+  const bool wide = a.N > 128;
+  return wide ? tc::dispatch_major<256>(a, a_mn, b_mn, lda, ldb) : tc::dispatch_major<128>(a, a_mn, b_mn, lda, ldb);
+}
+
+}  // namespace mt
+
+// diagnostic knob (tests / first hardware bring-up): 1 = converters write hi explicitly (default),
+// 0 = rely on the tensor core ignoring the low 13 mantissa bits of the raw fp32 operand.
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_write_hi(int v) {
+  tc::g_write_hi = v ? 1 : 0;
+  return MT_OK;
+}

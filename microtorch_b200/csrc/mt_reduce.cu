@@ -1,0 +1,254 @@
+// mt_reduce.cu - deterministic sum reductions over a [outer, red, inner] view (fp32).
+//
+// One primitive serves Reduce.sum (src/tensor/ops/reduce.py:11), the un-broadcast
+// reductions of BaseOps.bkwd_broadcast (src/tensor/ops/base.py:28-54) and - with the fused
+// `other` operand - the `grad * b.data` that precedes them in mul backward
+// (src/tensor/ops/overload.py:109-112), so the product is never written to HBM.
+//
+// HBM-bound: 4 B/element read (8 B with `other`), output negligible.  Structure: 128-bit
+// coalesced loads with four independent vectors in flight per thread, warp-shuffle
+// reduction, shared-memory tree across warps, and - when one pass cannot fill 148 SMs - a
+// split of the reduced axis across CTAs followed by a second tiny pass over the partials.
+// No float atomics: the summation tree is fixed by the shape, so results are reproducible.
+#include <algorithm>
+
+#include "mt_common.cuh"
+
+using namespace mt;
+
+namespace {
+
+constexpr int THREADS = 256;
+
+// ------------------------------------------------------------ inner == 1: rows
+// item = (row o, split s); the CTA sums x[o, r0:r1] (* w) and writes one partial.
+template <bool HAS_W, bool VEC>
+__global__ void __launch_bounds__(THREADS) reduce_rows_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                              long long outer, long long red, long long splits,
+                                                              long long chunk, const float* __restrict__ w,
+                                                              long long so, long long sr) {
+  __shared__ float smem[THREADS / 32];
+  const long long items = outer * splits;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long o = item / splits, s = item - o * splits;
+    const long long r0 = s * chunk;
+    long long r1 = r0 + chunk;
+    if (r1 > red) r1 = red;
+    const float* px = x + o * red;
+    const float* pw = HAS_W ? w + o * so : nullptr;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    if (VEC) {  // r0, red multiples of 4 and bases 16 B aligned (checked on the host)
+      const long long v0 = r0 >> 2, v1 = r1 >> 2;
+      long long i = v0 + threadIdx.x;
+      for (; i + 3 * THREADS < v1; i += 4 * THREADS) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a[u] = mtd::ld_stream4(px + 4 * (i + u * THREADS));
+          if (HAS_W) b[u] = mtd::ld_stream4(pw + 4 * (i + u * THREADS));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (HAS_W) {
+            acc0 += a[u].x * b[u].x; acc1 += a[u].y * b[u].y; acc2 += a[u].z * b[u].z; acc3 += a[u].w * b[u].w;
+          } else {
+            acc0 += a[u].x; acc1 += a[u].y; acc2 += a[u].z; acc3 += a[u].w;
+          }
+        }
+      }
+      for (; i < v1; i += THREADS) {
+        float4 a = mtd::ld_stream4(px + 4 * i);
+        if (HAS_W) {
+          float4 b = mtd::ld_stream4(pw + 4 * i);
+          acc0 += a.x * b.x; acc1 += a.y * b.y; acc2 += a.z * b.z; acc3 += a.w * b.w;
+        } else {
+          acc0 += a.x; acc1 += a.y; acc2 += a.z; acc3 += a.w;
+        }
+      }
+      for (long long j = (v1 << 2) + threadIdx.x; j < r1; j += THREADS)  // tail of the last split
+        acc0 += HAS_W ? px[j] * pw[j] : px[j];
+    } else {
+      for (long long j = r0 + threadIdx.x; j < r1; j += THREADS) acc0 += HAS_W ? px[j] * pw[j * sr] : px[j];
+    }
+    float t = mtd::block_sum<THREADS>((acc0 + acc1) + (acc2 + acc3), smem);
+    if (threadIdx.x == 0) out[item] = t;
+  }
+}
+
+// short rows: one warp per row
+template <bool HAS_W>
+__global__ void __launch_bounds__(THREADS) reduce_rows_warp_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                                   long long outer, long long red,
+                                                                   const float* __restrict__ w, long long so,
+                                                                   long long sr) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (THREADS / 32);
+  for (long long o = (long long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); o < outer; o += warps) {
+    const float* px = x + o * red;
+    float acc = 0.f;
+    for (long long j = lane; j < red; j += 32) acc += HAS_W ? px[j] * w[o * so + j * sr] : px[j];
+    acc = mtd::warp_sum(acc);
+    if (lane == 0) out[o] = acc;
+  }
+}
+
+// ------------------------------------------------------------ inner > 1: columns
+// block = TX column-vectors x TY row lanes; grid = (column tiles, splits, outer tiles)
+constexpr int TX = 64, TY = 4;
+
+template <bool HAS_W, int V>
+__global__ void __launch_bounds__(TX* TY) reduce_cols_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                             long long outer, long long red, long long inner,
+                                                             long long splits, long long chunk,
+                                                             const float* __restrict__ w, long long so, long long sr,
+                                                             long long si) {
+  __shared__ float smem[TY][TX * V + 1];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const long long col = ((long long)blockIdx.x * TX + tx) * V;
+  const long long s = blockIdx.y;
+  const long long r0 = s * chunk;
+  long long r1 = r0 + chunk;
+  if (r1 > red) r1 = red;
+  for (long long o = blockIdx.z; o < outer; o += gridDim.z) {
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    if (col < inner) {
+      const float* px = x + (o * red) * inner + col;
+      const float* pw = HAS_W ? w + o * so + col * si : nullptr;
+      long long r = r0 + ty;
+      if (V == 4) {
+        for (; r + 3 * TY < r1; r += 4 * TY) {
+          float4 a[4], b[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            a[u] = mtd::ld_stream4(px + (r + u * TY) * inner);
+            if (HAS_W) b[u] = mtd::ld_stream4(pw + (r + u * TY) * sr);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (HAS_W) {
+              acc[0] += a[u].x * b[u].x; acc[1] += a[u].y * b[u].y; acc[2] += a[u].z * b[u].z; acc[3] += a[u].w * b[u].w;
+            } else {
+              acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
+            }
+          }
+        }
+        for (; r < r1; r += TY) {
+          float4 a = mtd::ld_stream4(px + r * inner);
+          if (HAS_W) {
+            float4 b = mtd::ld_stream4(pw + r * sr);
+            acc[0] += a.x * b.x; acc[1] += a.y * b.y; acc[2] += a.z * b.z; acc[3] += a.w * b.w;
+          } else {
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+          }
+        }
+      } else {
+        for (; r < r1; r += TY) acc[0] += HAS_W ? px[r * inner] * pw[r * sr] : px[r * inner];
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) smem[ty][tx * V + v] = acc[v];
+    __syncthreads();
+    if (ty == 0 && col < inner) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float t = (smem[0][tx * V + v] + smem[1][tx * V + v]) + (smem[2][tx * V + v] + smem[3][tx * V + v]);
+        out[(o * splits + s) * inner + col + v] = t;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int reduce_rows(float* out, const float* x, long long outer, long long red, const float* w, long long so, long long sr) {
+  cudaStream_t st = g().stream;
+  const int sms = g().sm_count;
+  if (red <= 256 && outer >= 64) {
+    const int grid = (int)std::min<long long>(ceil_div(outer, THREADS / 32), (long long)sms * 16);
+    if (w) reduce_rows_warp_kernel<true><<<grid, THREADS, 0, st>>>(out, x, outer, red, w, so, sr);
+    else reduce_rows_warp_kernel<false><<<grid, THREADS, 0, st>>>(out, x, outer, red, w, so, sr);
+    MT_LAUNCHED();
+    return MT_OK;
+  }
+  long long splits = 1;
+  if (outer < 2LL * sms) {
+    splits = std::min<long long>(ceil_div(4LL * sms, outer), ceil_div(red, 4096));
+    if (splits < 1) splits = 1;
+  }
+  long long chunk = ceil_div(red, splits);
+  chunk = (chunk + 3) & ~3LL;
+  splits = ceil_div(red, chunk);
+  const bool vec = aligned16(x) && red % 4 == 0 && (!w || (aligned16(w) && sr == 1 && so % 4 == 0));
+  float* dst = out;
+  float* partial = nullptr;
+  if (splits > 1) {
+    int rc = pool_alloc((void**)&partial, sizeof(float) * outer * splits);
+    if (rc) return rc;
+    dst = partial;
+  }
+  const int grid = (int)std::min<long long>(outer * splits, (long long)sms * 8);
+#define MT_ROWS(HW, VC) reduce_rows_kernel<HW, VC><<<grid, THREADS, 0, st>>>(dst, x, outer, red, splits, chunk, w, so, sr)
+  if (w) { if (vec) MT_ROWS(true, true); else MT_ROWS(true, false); }
+  else { if (vec) MT_ROWS(false, true); else MT_ROWS(false, false); }
+#undef MT_ROWS
+  MT_LAUNCHED();
+  if (splits > 1) {
+    int rc = reduce_rows(out, partial, outer, splits, nullptr, 0, 0);
+    pool_free(partial);  // stream-ordered: the second pass was queued before any reuse
+    return rc;
+  }
+  return MT_OK;
+}
+
+int reduce_cols(float* out, const float* x, long long outer, long long red, long long inner, const float* w,
+                long long so, long long sr, long long si) {
+  cudaStream_t st = g().stream;
+  const int sms = g().sm_count;
+  const bool vec = inner % 4 == 0 && aligned16(x) && (!w || (aligned16(w) && si == 1 && sr % 4 == 0 && so % 4 == 0));
+  const int V = vec ? 4 : 1;
+  const long long tiles = ceil_div(inner, (long long)TX * V);
+  const long long oz = std::min<long long>(outer, 65535);
+  long long splits = 1;
+  if (tiles * oz < 4LL * sms) {
+    splits = std::min<long long>(ceil_div(4LL * sms, tiles * oz), ceil_div(red, 64));
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+  }
+  const long long chunk = ceil_div(red, splits);
+  splits = ceil_div(red, chunk);
+  float* dst = out;
+  float* partial = nullptr;
+  if (splits > 1) {
+    int rc = pool_alloc((void**)&partial, sizeof(float) * outer * splits * inner);
+    if (rc) return rc;
+    dst = partial;
+  }
+  dim3 grid((unsigned)tiles, (unsigned)splits, (unsigned)oz);
+#define MT_COLS(HW, VV) reduce_cols_kernel<HW, VV><<<grid, TX * TY, 0, st>>>(dst, x, outer, red, inner, splits, chunk, w, so, sr, si)
+  if (w) { if (vec) MT_COLS(true, 4); else MT_COLS(true, 1); }
+  else { if (vec) MT_COLS(false, 4); else MT_COLS(false, 1); }
+#undef MT_COLS
+  MT_LAUNCHED();
+  if (splits > 1) {
+    int rc = reduce_cols(out, partial, outer, splits, inner, nullptr, 0, 0, 0);
+    pool_free(partial);
+    return rc;
+  }
+  return MT_OK;
+}
+
+}  // namespace
+
+MT_API int mt_reduce_sum_f32(float* out, const float* x, int64_t outer, int64_t red, int64_t inner, const float* other,
+                             int64_t so, int64_t sr, int64_t si) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(out && x, "mt_reduce_sum_f32: null pointer");
+  MT_CHECK_ARG(outer >= 0 && red >= 0 && inner >= 0, "mt_reduce_sum_f32: negative extent");
+  if (outer * inner == 0) return MT_OK;
+  if (red == 0) return mt_memset_zero(out, sizeof(float) * outer * inner);
+  if (inner == 1) return reduce_rows(out, x, outer, red, other, so, sr);
+  return reduce_cols(out, x, outer, red, inner, other, so, sr, si);
+}

@@ -1,0 +1,539 @@
+// mt_runtime.cu - process state, caching device pool, copies, events.
+// Replaces CuPy's context/stream/MemoryPool for MicroTorch's device="cuda" path
+// (reference: src/tensor/device.py:7-11,74-84; src/tensor/tensor.py:77,205,218-221).
+#include <stdarg.h>
+
+#include "mt_common.cuh"
+
+namespace mt {
+
+Global& g() {
+  static Global G;
+  return G;
+}
+
+static thread_local char tl_error[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int status, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+  va_end(ap);
+  return status;
+}
+
+// ------------------------------------------------------------------ caching pool
+// Size-class free lists.  All library work is ordered on one compute stream, so a block
+// returned by mt_free can be handed out again immediately: any kernel still reading it was
+// queued earlier on the same stream than whatever the new owner queues ("stream-ordered
+// reuse").  The communication stream only touches gradient buffers that stay owned across
+// the collective (mt_comm_wait orders them back).
+struct Pool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;  // rounded size -> block
+  std::map<void*, size_t> live;              // block -> rounded size
+  size_t reserved = 0, in_use = 0, peak = 0;
+  uint64_t n_req = 0, n_dev = 0;
+};
+static Pool& pool() {
+  static Pool P;
+  return P;
+}
+
+static size_t round_size(size_t b) {
+  if (b == 0) b = 1;
+  if (b <= (1u << 20)) return (b + 511) & ~size_t(511);          // 512 B classes below 1 MiB
+  return (b + ((2u << 20) - 1)) & ~size_t((2u << 20) - 1);       // 2 MiB classes above
+}
+
+int pool_alloc(void** out, size_t bytes) {
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  const size_t want = round_size(bytes);
+  P.n_req++;
+  auto it = P.free_blocks.lower_bound(want);
+  // accept a cached block up to 12.5% larger (bounded internal fragmentation)
+  if (it != P.free_blocks.end() && it->first <= want + want / 8) {
+    void* p = it->second;
+    size_t sz = it->first;
+    P.free_blocks.erase(it);
+    P.live[p] = sz;
+    P.in_use += sz;
+    if (P.in_use > P.peak) P.peak = P.in_use;
+    *out = p;
+    return MT_OK;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    // release every cached block and retry once
+    cudaStreamSynchronize(g().stream);
+    for (auto& kv : P.free_blocks) {
+      cudaFree(kv.second);
+      P.reserved -= kv.first;
+    }
+    P.free_blocks.clear();
+    e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(MT_ERR_OOM, "mt_malloc: cudaMalloc(%zu) failed: %s (reserved %zu, in use %zu)", want,
+                  cudaGetErrorString(e), P.reserved, P.in_use);
+    }
+  }
+  P.n_dev++;
+  P.reserved += want;
+  P.live[p] = want;
+  P.in_use += want;
+  if (P.in_use > P.peak) P.peak = P.in_use;
+  *out = p;
+  return MT_OK;
+}
+
+int pool_free(void* p) {
+  if (!p) return MT_OK;
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  auto it = P.live.find(p);
+  if (it == P.live.end()) return fail(MT_ERR_INVALID, "mt_free: %p was not allocated by mt_malloc", p);
+  size_t sz = it->second;
+  P.live.erase(it);
+  P.in_use -= sz;
+  P.free_blocks.emplace(sz, p);
+  return MT_OK;
+}
+
+}  // namespace mt
+
+using namespace mt;
+
+MT_API const char* mt_last_error(void) { return tl_error; }
+MT_API const char* mt_version(void) { return "microtorch_b200 0.1.0 (sm_100a)"; }
+
+MT_API int mt_device_count(int* count) {
+  MT_CHECK_ARG(count, "mt_device_count: null out pointer");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *count = 0;
+    return fail(MT_ERR_CUDA, "mt_device_count: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return MT_OK;
+}
+
+MT_API int mt_is_initialized(void) { return g().ready ? 1 : 0; }
+
+MT_API int mt_init(int device) {
+  Global& G = g();
+  if (G.ready) {
+    if (G.device == device) return MT_OK;
+    return fail(MT_ERR_INVALID, "mt_init: already initialised on device %d (one process per GPU)", G.device);
+  }
+  int n = 0;
+  MT_CUDA(cudaGetDeviceCount(&n));
+  MT_CHECK_ARG(device >= 0 && device < n, "mt_init: device %d out of range (%d visible)", device, n);
+  MT_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MT_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(MT_ERR_UNSUPPORTED, "mt_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                device, prop.major, prop.minor);
+  G.device = device;
+  G.sm_count = prop.multiProcessorCount;
+  G.cc_major = prop.major;
+  G.cc_minor = prop.minor;
+  G.hbm_bytes = prop.totalGlobalMem;
+  G.l2_bytes = (size_t)prop.l2CacheSize;
+  MT_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  MT_CUDA(cudaStreamCreateWithFlags(&G.comm_stream, cudaStreamNonBlocking));
+  MT_CUDA(cudaEventCreateWithFlags(&G.ev_compute, cudaEventDisableTiming));
+  MT_CUDA(cudaEventCreateWithFlags(&G.ev_comm, cudaEventDisableTiming));
+  G.launches = 0;
+  G.ready = true;
+  return MT_OK;
+}
+
+MT_API int mt_shutdown(void) {
+  Global& G = g();
+  if (!G.ready) return MT_OK;
+  cudaDeviceSynchronize();
+  mt_pool_trim();
+  if (G.l2_flush_buf) cudaFree(G.l2_flush_buf);
+  G.l2_flush_buf = nullptr;
+  cudaEventDestroy(G.ev_compute);
+  cudaEventDestroy(G.ev_comm);
+  cudaStreamDestroy(G.stream);
+  cudaStreamDestroy(G.comm_stream);
+  G.ready = false;
+  return MT_OK;
+}
+
+MT_API int mt_device_info(char* name, size_t cap, int* sm_count, size_t* hbm_bytes, int* cc_major, int* cc_minor) {
+  MT_REQUIRE_INIT();
+  cudaDeviceProp prop;
+  MT_CUDA(cudaGetDeviceProperties(&prop, g().device));
+  if (name && cap) {
+    strncpy(name, prop.name, cap - 1);
+    name[cap - 1] = 0;
+  }
+  if (sm_count) *sm_count = g().sm_count;
+  if (hbm_bytes) *hbm_bytes = g().hbm_bytes;
+  if (cc_major) *cc_major = g().cc_major;
+  if (cc_minor) *cc_minor = g().cc_minor;
+  return MT_OK;
+}
+
+MT_API int mt_sync(void) {
+  MT_REQUIRE_INIT();
+  MT_CUDA(cudaStreamSynchronize(g().stream));
+  MT_CUDA(cudaStreamSynchronize(g().comm_stream));
+  return MT_OK;
+}
+
+MT_API int mt_stream(void** s) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(s, "mt_stream: null out pointer");
+  *s = (void*)g().stream;
+  return MT_OK;
+}
+
+MT_API int mt_event_create(void** ev) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(ev, "mt_event_create: null out pointer");
+  cudaEvent_t e;
+  MT_CUDA(cudaEventCreate(&e));
+  *ev = (void*)e;
+  return MT_OK;
+}
+MT_API int mt_event_record(void* ev) {
+  MT_REQUIRE_INIT();
+  MT_CUDA(cudaEventRecord((cudaEvent_t)ev, g().stream));
+  return MT_OK;
+}
+MT_API int mt_event_sync(void* ev) {
+  MT_REQUIRE_INIT();
+  MT_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
+  return MT_OK;
+}
+MT_API int mt_event_elapsed_ms(void* a, void* b, float* ms) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(ms, "mt_event_elapsed_ms: null out pointer");
+  MT_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return MT_OK;
+}
+MT_API int mt_event_destroy(void* ev) {
+  MT_REQUIRE_INIT();
+  MT_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  return MT_OK;
+}
+
+MT_API int mt_launch_count(uint64_t* c) {
+  MT_CHECK_ARG(c, "mt_launch_count: null out pointer");
+  *c = g().launches;
+  return MT_OK;
+}
+MT_API int mt_launch_count_reset(void) {
+  g().launches = 0;
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------ memory
+MT_API int mt_malloc(void** p, size_t bytes) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(p, "mt_malloc: null out pointer");
+  return pool_alloc(p, bytes);
+}
+MT_API int mt_free(void* p) {
+  if (!g().ready) return MT_OK;  // interpreter teardown after mt_shutdown: nothing left to return
+  return pool_free(p);
+}
+
+MT_API int mt_pool_stats(size_t* reserved, size_t* in_use, size_t* peak, uint64_t* n_req, uint64_t* n_dev) {
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  if (reserved) *reserved = P.reserved;
+  if (in_use) *in_use = P.in_use;
+  if (peak) *peak = P.peak;
+  if (n_req) *n_req = P.n_req;
+  if (n_dev) *n_dev = P.n_dev;
+  return MT_OK;
+}
+
+MT_API int mt_pool_trim(void) {
+  if (!g().ready) return MT_OK;
+  Pool& P = pool();
+  cudaStreamSynchronize(g().stream);
+  std::lock_guard<std::mutex> lk(P.mu);
+  for (auto& kv : P.free_blocks) {
+    cudaFree(kv.second);
+    P.reserved -= kv.first;
+  }
+  P.free_blocks.clear();
+  return MT_OK;
+}
+
+MT_API int mt_host_alloc(void** p, size_t bytes) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(p, "mt_host_alloc: null out pointer");
+  MT_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+  return MT_OK;
+}
+MT_API int mt_host_free(void* p) {
+  if (!g().ready || !p) return MT_OK;
+  MT_CUDA(cudaFreeHost(p));
+  return MT_OK;
+}
+
+MT_API int mt_h2d(void* dst, const void* src, size_t bytes) {
+  MT_REQUIRE_INIT();
+  if (!bytes) return MT_OK;
+  MT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g().stream));
+  MT_CUDA(cudaStreamSynchronize(g().stream));  // pageable source: caller may reuse it at once
+  return MT_OK;
+}
+MT_API int mt_d2h(void* dst, const void* src, size_t bytes) {
+  MT_REQUIRE_INIT();
+  if (!bytes) return MT_OK;
+  MT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g().stream));
+  MT_CUDA(cudaStreamSynchronize(g().stream));
+  return MT_OK;
+}
+MT_API int mt_h2d_async(void* dst, const void* src, size_t bytes) {
+  MT_REQUIRE_INIT();
+  if (!bytes) return MT_OK;
+  MT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g().stream));
+  return MT_OK;
+}
+MT_API int mt_d2h_async(void* dst, const void* src, size_t bytes) {
+  MT_REQUIRE_INIT();
+  if (!bytes) return MT_OK;
+  MT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g().stream));
+  return MT_OK;
+}
+MT_API int mt_d2d(void* dst, const void* src, size_t bytes) {
+  MT_REQUIRE_INIT();
+  if (!bytes) return MT_OK;
+  MT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g().stream));
+  return MT_OK;
+}
+MT_API int mt_memset_zero(void* p, size_t bytes) {
+  MT_REQUIRE_INIT();
+  if (!bytes) return MT_OK;
+  MT_CUDA(cudaMemsetAsync(p, 0, bytes, g().stream));
+  return MT_OK;
+}
+
+// one launch zeroing many buffers (Module.zero_grad over all parameters, module.py:83-89)
+struct ZeroTable {
+  enum { CAP = 96 };
+  float* ptr[CAP];
+  unsigned long long n4[CAP];   // float4 count (buffers are pool blocks: 512 B granularity)
+  unsigned long long start[CAP + 1];
+};
+__global__ void __launch_bounds__(256) zero_multi_kernel(const __grid_constant__ ZeroTable t, int count) {
+  const unsigned long long total = t.start[count];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  int cur = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    while (i >= t.start[cur + 1]) ++cur;
+    reinterpret_cast<float4*>(t.ptr[cur])[i - t.start[cur]] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+MT_API int mt_memset_multi(void* const* ptrs, const size_t* bytes, int count) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(count >= 0, "mt_memset_multi: negative count");
+  int done = 0;
+  while (done < count) {
+    ZeroTable t;
+    int k = 0;
+    unsigned long long acc = 0;
+    while (done < count && k < ZeroTable::CAP) {
+      size_t b = bytes[done];
+      MT_CHECK_ARG((reinterpret_cast<uintptr_t>(ptrs[done]) & 15) == 0, "mt_memset_multi: pointer %d not 16 B aligned", done);
+      if (b % 16) {  // odd tail: plain memset for this one (rare: parameters are multiples of 4 floats)
+        MT_CUDA(cudaMemsetAsync(ptrs[done], 0, b, g().stream));
+      } else if (b) {
+        t.ptr[k] = (float*)ptrs[done];
+        t.n4[k] = b / 16;
+        t.start[k] = acc;
+        acc += t.n4[k];
+        ++k;
+      }
+      ++done;
+    }
+    t.start[k] = acc;
+    if (k == 0) continue;
+    int grid = ew_grid((int64_t)acc, 256 * 4);
+    zero_multi_kernel<<<grid, 256, 0, g().stream>>>(t, k);
+    MT_LAUNCHED();
+  }
+  return MT_OK;
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ out, size_t n, float v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = n / 4;
+  const float4 v4 = make_float4(v, v, v, v);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    reinterpret_cast<float4*>(out)[i] = v4;
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+
+MT_API int mt_fill_f32(float* out, size_t n, float value) {
+  MT_REQUIRE_INIT();
+  if (!n) return MT_OK;
+  fill_kernel<<<ew_grid((int64_t)n / 4 + 1, 256 * 4), 256, 0, g().stream>>>(out, n, value);
+  MT_LAUNCHED();
+  return MT_OK;
+}
+
+MT_API int mt_l2_flush(void) {
+  MT_REQUIRE_INIT();
+  Global& G = g();
+  if (!G.l2_flush_buf) {
+    G.l2_flush_bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+    MT_CUDA(cudaMalloc(&G.l2_flush_buf, G.l2_flush_bytes));
+  }
+  MT_CUDA(cudaMemsetAsync(G.l2_flush_buf, 0, G.l2_flush_bytes, G.stream));
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------ strided copies
+struct StridedDesc {
+  int ndim;
+  long long shape[MT_MAX_DIMS];
+  long long stride[MT_MAX_DIMS];
+};
+
+// gather: out (contiguous) <- in (strided).  Inner-most dimension handled by consecutive
+// threads so reads are coalesced whenever the inner stride is 1.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) strided_copy_kernel(float* __restrict__ dense, float* strided,
+                                                           const __grid_constant__ StridedDesc d, long long total) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    long long rem = i, off = 0;
+#pragma unroll 1
+    for (int k = d.ndim - 1; k >= 0; --k) {
+      long long q = rem / d.shape[k];
+      off += (rem - q * d.shape[k]) * d.stride[k];
+      rem = q;
+    }
+    if (SCATTER)
+      strided[off] = dense[i];
+    else
+      dense[i] = strided[off];
+  }
+}
+
+static int make_desc(StridedDesc& d, int ndim, const int64_t* shape, const int64_t* strides, long long& total,
+                     const char* who) {
+  MT_CHECK_ARG(ndim >= 0 && ndim <= MT_MAX_DIMS, "%s: ndim %d out of range", who, ndim);
+  d.ndim = ndim;
+  total = 1;
+  for (int k = 0; k < ndim; ++k) {
+    MT_CHECK_ARG(shape[k] >= 0, "%s: negative extent", who);
+    d.shape[k] = shape[k];
+    d.stride[k] = strides[k];
+    total *= shape[k];
+  }
+  return MT_OK;
+}
+
+MT_API int mt_copy_strided_f32(float* out, const float* in, int ndim, const int64_t* shape, const int64_t* in_strides) {
+  MT_REQUIRE_INIT();
+  StridedDesc d;
+  long long total;
+  int rc = make_desc(d, ndim, shape, in_strides, total, "mt_copy_strided_f32");
+  if (rc) return rc;
+  if (total == 0) return MT_OK;
+  strided_copy_kernel<false><<<ew_grid(total, 256 * 4), 256, 0, g().stream>>>(out, const_cast<float*>(in), d, total);
+  MT_LAUNCHED();
+  return MT_OK;
+}
+
+MT_API int mt_scatter_strided_f32(float* out, const int64_t* out_strides, const float* in, int ndim,
+                                  const int64_t* shape) {
+  MT_REQUIRE_INIT();
+  StridedDesc d;
+  long long total;
+  int rc = make_desc(d, ndim, shape, out_strides, total, "mt_scatter_strided_f32");
+  if (rc) return rc;
+  if (total == 0) return MT_OK;
+  strided_copy_kernel<true><<<ew_grid(total, 256 * 4), 256, 0, g().stream>>>(const_cast<float*>(in), out, d, total);
+  MT_LAUNCHED();
+  return MT_OK;
+}
+
+// ------------------------------------------------------------------ row gather / scatter-assign
+__global__ void __launch_bounds__(256) gather_rows_kernel(float* __restrict__ out, const float* __restrict__ in,
+                                                          const long long* __restrict__ idx, long long n_index,
+                                                          long long row, long long n_rows) {
+  const long long total = n_index * row;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    long long r = i / row, c = i - r * row;
+    long long src = idx[r];
+    if (src < 0) src += n_rows;
+    out[i] = in[src * row + c];
+  }
+}
+
+// NumPy assigns duplicates in order, so the LAST occurrence of an index wins.  A position
+// writes its row only if no later position carries the same index; the check is a scan of the
+// (short) index list, done once per row by thread 0 of the block and shared through smem.
+__global__ void __launch_bounds__(256) scatter_rows_assign_kernel(float* __restrict__ out, const float* __restrict__ in,
+                                                                  const long long* __restrict__ idx, long long n_index,
+                                                                  long long row, long long n_rows) {
+  __shared__ int winner;
+  for (long long r = blockIdx.x; r < n_index; r += gridDim.x) {
+    long long dst = idx[r];
+    if (dst < 0) dst += n_rows;
+    if (threadIdx.x == 0) {
+      int w = 1;
+      for (long long j = r + 1; j < n_index; ++j) {
+        long long o = idx[j];
+        if (o < 0) o += n_rows;
+        if (o == dst) {
+          w = 0;
+          break;
+        }
+      }
+      winner = w;
+    }
+    __syncthreads();
+    if (winner)
+      for (long long c = threadIdx.x; c < row; c += blockDim.x) out[dst * row + c] = in[r * row + c];
+    __syncthreads();
+  }
+}
+
+MT_API int mt_gather_rows_f32(float* out, const float* in, const int64_t* idx, int64_t n_index, int64_t row,
+                              int64_t n_rows) {
+  MT_REQUIRE_INIT();
+  if (n_index * row == 0) return MT_OK;
+  gather_rows_kernel<<<ew_grid(n_index * row, 256 * 4), 256, 0, g().stream>>>(out, in, (const long long*)idx, n_index,
+                                                                             row, n_rows);
+  MT_LAUNCHED();
+  return MT_OK;
+}
+
+MT_API int mt_scatter_rows_assign_f32(float* out, const float* in, const int64_t* idx, int64_t n_index, int64_t row,
+                                      int64_t n_rows) {
+  MT_REQUIRE_INIT();
+  if (n_index * row == 0) return MT_OK;
+  int grid = (int)(n_index < (int64_t)g().sm_count * 8 ? n_index : (int64_t)g().sm_count * 8);
+  scatter_rows_assign_kernel<<<grid, 256, 0, g().stream>>>(out, in, (const long long*)idx, n_index, row, n_rows);
+  MT_LAUNCHED();
+  return MT_OK;
+}

@@ -13,12 +13,17 @@
 // the swizzle - then hand the stage to the single MMA-issuing thread.  The backward prologue
 // dZ = dY * (1 - Y^2) is fused into the same pass (the Y tile is TMA-loaded into the lo buffer).
 //
-// CTA = 10 warps, persistent over output tiles (grid = #SMs), 128 x BN x 32 tiles:
+// CTA = 16 warps (4 warpgroups), persistent over output tiles (grid = #SMs), 128 x BN x 32 tiles:
 //   warp 0      TMA producer      (one lane)            full[s]  <- bytes landed
-//   warps 2-5   converters        (128 threads)         conv[s]  <- hi/lo ready (generic->async proxy fence)
-//   warp 1      MMA issuer        (one lane) + TMEM     empty[s] <- tcgen05.commit, tfull[a] <- tile done
-//   warps 6-9   epilogue          (128 threads)         tempty[a] <- accumulator drained
-// Two TMEM accumulators (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//   warp 1      MMA issuer        (one lane) + TMEM     empty[s] <- tcgen05.commit, tfull[a] <- chunk done
+//   warps 4-7   converters        (128 threads)         conv[s]  <- hi/lo ready (generic->async proxy fence)
+//   warps 8-15  accumulate/epilogue (256 threads)       tempty[a] <- accumulator drained
+// The tensor core adds into its fp32 TMEM accumulator with truncation (measured: error grows
+// linearly, ~2^-24 per tcgen05.mma, 7.5e-5 at K=4096), so K is cut into chunks of CHUNK_KB
+// k-blocks: each chunk accumulates into one of two TMEM buffers (ping-pong) and the epilogue
+// warps fold finished chunks into IEEE fp32 running sums held in registers (setmaxnreg gives
+// them 200 registers, the data-movement warps 56).  Chunk c+1's MMAs overlap chunk c's drain
+// and the previous tile's bias/tanh/store epilogue.
 // Operands may be K-major or MN-major (UMMA descriptor transpose bits), so forward (X.W^T), dX
 // (dZ.W) and dW (dZ^T.X) all read the row-major activations/weights in place - no transposes.
 //
@@ -38,8 +43,10 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;            // 32 fp32 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;         // kind::tf32: 32 B of K per instruction
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 512;  // 4 warpgroups
 constexpr int NUM_ACC = 2;
+constexpr int REGS_MOVERS = 56;   // producer / MMA / converter warpgroups
+constexpr int REGS_EPILOGUE = 200;
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,13 +72,22 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 // Bounded wait: a protocol bug must end in a trap (a clean CUDA error), never in a hung GPU.
+// No printf / no calls here: a real call makes ptxas size the whole kernel for the smallest
+// setmaxnreg budget (observed: 53 registers and the running sums spilled to local memory).
+// The culprit is left in a host-mapped word instead (mt_gemm_tc_debug_word()).
+__device__ int* g_dbg_word = nullptr;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-      printf("mt_gemm_tc: mbarrier wait timed out (role %d, block %d, thread %d, parity %u)\n", who, blockIdx.x,
-             threadIdx.x, parity);
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s
+      if (g_dbg_word) {
+        g_dbg_word[0] = 0x7100 | who;
+        g_dbg_word[1] = blockIdx.x;
+        g_dbg_word[2] = threadIdx.x;
+        g_dbg_word[3] = parity;
+        __threadfence_system();
+      }
       __trap();
     }
   }
@@ -120,14 +136,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 
 // ---------------------------------------------------------------- descriptors
-// Shared-memory matrix descriptor (SM100 format, version 1), SWIZZLE_128B.
-//   K-major : rows of 128 B, 8-row atoms 1024 B apart (SBO); LBO unused (encoded 1).
-//   MN-major: 32-element (128 B) MN atoms 4096 B apart (LBO = one 32x32 TMA box), k-groups of 8 at SBO = 1024 B.
+// Shared-memory matrix descriptor (SM100 format, version 1).
+//   K-major : SWIZZLE_128B (type 2).  Rows of 128 B (32 k), 8-row atoms 1024 B apart (SBO); LBO unused (1).
+//             One UMMA_K slice = 32 B further along the row.
+//   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (type 1; TMA: SWIZZLE_128B_ATOM_32B).
+//             A 32(mn) x 32(k) TMA box is 32 rows of 128 B; 4-row k-atoms 512 B apart (SBO), 32-element
+//             MN atoms one box = 4096 B apart (LBO).  One UMMA_K slice (8 k) = 1024 B further.
 __host__ __device__ constexpr uint64_t make_smem_desc_base(bool mn_major) {
-  return (uint64_t(mn_major ? (4096 >> 4) : 1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
-         (uint64_t(2) << 61);
+  return mn_major ? ((uint64_t(4096 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(1) << 61))
+                  : ((uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61));
 }
 __device__ __forceinline__ uint64_t smem_desc(uint64_t base, uint32_t addr) {
   return base | uint64_t((addr & 0x3FFFFu) >> 4);
@@ -144,8 +167,9 @@ struct Params {
   long long M, N, K;
   int act, accumulate;
   int m_blocks, n_blocks, k_blocks;
+  int chunk_kb;       // k-blocks accumulated in TMEM before a flush to the fp32 register sums
   int has_prologue;   // A' = A * (1 - T^2)
-  int write_hi;       // converters store hi explicitly (else rely on the MMA ignoring the low 13 bits)
+  int write_hi;       // converters store hi explicitly (else the MMA's own truncation of the raw fp32 is hi)
 };
 
 template <int BN>
@@ -156,9 +180,11 @@ struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = (NUM_ACC * BN <= 256) ? 256 : 512;
+  static constexpr int EPI_COLS = BN / 2;               // accumulator columns per epilogue thread
 };
 
-// hi/lo split of one 16-byte vector.  RN=true rounds hi to nearest tf32 (needs the explicit hi store).
+// hi/lo split of one 16-byte vector.  RN=true rounds hi to nearest tf32 (needs the explicit hi store);
+// RN=false leaves hi = truncation, which is what the tensor core itself does with the raw fp32 bits.
 template <bool RN>
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   const uint32_t add = RN ? 0x1000u : 0u;
@@ -204,7 +230,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     fence_barrier_init();
   }
@@ -216,186 +242,204 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int num_tiles = p.m_blocks * p.n_blocks;
   const int kb_count = p.k_blocks;
+  const int chunk_kb = p.chunk_kb;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+  if (warp < 8) {
+    reg_dec<REGS_MOVERS>();
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx_bytes = C::A_TILE + C::B_TILE + (p.has_prologue ? C::A_TILE : 0);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+          for (int kb = 0; kb < kb_count; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1, 0);
+            const uint32_t sa = smem_base + stage * C::STAGE;
+            const uint32_t sb = sa + C::A_TILE;
+            const uint32_t sa_lo = sb + C::B_TILE;
+            const uint32_t fb = full_bar(stage);
+            mbar_expect_tx(fb, tx_bytes);
+            const int k0 = kb * BK;
+            if (A_MN) {
+#pragma unroll
+              for (int j = 0; j < BM / 32; ++j) {   // 32(m) x 32(k) boxes, 4096 B each
+                tma_load_2d(sa + j * 4096, &map_a, fb, m0 + j * 32, k0);
+                if (p.has_prologue) tma_load_2d(sa_lo + j * 4096, &map_t, fb, m0 + j * 32, k0);
+              }
+            } else {
+              tma_load_2d(sa, &map_a, fb, k0, m0);    // 32(k) x 128(m) box
+              if (p.has_prologue) tma_load_2d(sa_lo, &map_t, fb, k0, m0);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, fb, n0 + j * 32, k0);
+            } else {
+              tma_load_2d(sb, &map_b, fb, k0, n0);
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+        constexpr uint64_t adesc_base = make_smem_desc_base(A_MN);
+        constexpr uint64_t bdesc_base = make_smem_desc_base(B_MN);
+        constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;   // bytes per UMMA_K slice
+        constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t cc = 0;                                   // chunk counter across tiles -> TMEM buffer + phase
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          for (int kb0 = 0; kb0 < kb_count; kb0 += chunk_kb, ++cc) {
+            const int acc = cc & 1;
+            mbar_wait(tempty_bar(acc), ((cc >> 1) & 1) ^ 1, 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            const int kb1 = min(kb0 + chunk_kb, kb_count);
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(conv_bar(stage), phase, 2);
+              tc_fence_after();
+              const uint32_t sa = smem_base + stage * C::STAGE;
+              const uint32_t sb = sa + C::A_TILE;
+              const uint32_t sa_lo = sb + C::B_TILE;
+              const uint32_t sb_lo = sa_lo + C::A_TILE;
+#pragma unroll
+              for (int j = 0; j < BK / UMMA_K; ++j) {
+                const uint64_t a_hi = smem_desc(adesc_base, sa + j * a_kstep);
+                const uint64_t a_lo = smem_desc(adesc_base, sa_lo + j * a_kstep);
+                const uint64_t b_hi = smem_desc(bdesc_base, sb + j * b_kstep);
+                const uint64_t b_lo = smem_desc(bdesc_base, sb_lo + j * b_kstep);
+                umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb > kb0) || (j > 0));   // small terms first
+                umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+              }
+              umma_commit(empty_bar(stage));               // stage reusable once these MMAs retire
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull_bar(acc));                   // chunk accumulator complete
+          }
+        }
+      }
+    } else if (warp >= 4) {
+      // ===================== converters (warps 4..7, 128 threads) =====================
+      const int ct = threadIdx.x - 128;
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = C::A_TILE + C::B_TILE + (p.has_prologue ? C::A_TILE : 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
         for (int kb = 0; kb < kb_count; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1, 0);
-          const uint32_t sa = smem_base + stage * C::STAGE;
-          const uint32_t sb = sa + C::A_TILE;
-          const uint32_t sa_lo = sb + C::B_TILE;
-          const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, tx_bytes);
-          const int k0 = kb * BK;
-          if (A_MN) {
-#pragma unroll
-            for (int j = 0; j < BM / 32; ++j) {   // 32(m) x 32(k) boxes, 4096 B each
-              tma_load_2d(sa + j * 4096, &map_a, fb, m0 + j * 32, k0);
-              if (p.has_prologue) tma_load_2d(sa_lo + j * 4096, &map_t, fb, m0 + j * 32, k0);
+          mbar_wait(full_bar(stage), phase, 3);
+          uint8_t* sa = smem_gen + stage * C::STAGE;
+          uint8_t* sb = sa + C::A_TILE;
+          uint8_t* sa_lo = sb + C::B_TILE;
+          uint8_t* sb_lo = sa_lo + C::A_TILE;
+          if (p.has_prologue) {
+#pragma unroll 4
+            for (int i = ct; i < C::A_TILE / 16; i += 128) {
+              const float4 g = reinterpret_cast<float4*>(sa)[i];
+              const float4 y = reinterpret_cast<float4*>(sa_lo)[i];
+              float4 z, hi, lo;
+              z.x = __fmul_rn(g.x, __fsub_rn(1.f, __fmul_rn(y.x, y.x)));
+              z.y = __fmul_rn(g.y, __fsub_rn(1.f, __fmul_rn(y.y, y.y)));
+              z.z = __fmul_rn(g.z, __fsub_rn(1.f, __fmul_rn(y.z, y.z)));
+              z.w = __fmul_rn(g.w, __fsub_rn(1.f, __fmul_rn(y.w, y.w)));
+              split4<false>(z, hi, lo);
+              reinterpret_cast<float4*>(sa)[i] = z;        // the MMA truncates z itself
+              reinterpret_cast<float4*>(sa_lo)[i] = lo;
+            }
+          } else if (p.write_hi) {
+#pragma unroll 4
+            for (int i = ct; i < C::A_TILE / 16; i += 128) {
+              float4 hi, lo;
+              split4<true>(reinterpret_cast<float4*>(sa)[i], hi, lo);
+              reinterpret_cast<float4*>(sa)[i] = hi;
+              reinterpret_cast<float4*>(sa_lo)[i] = lo;
             }
           } else {
-            tma_load_2d(sa, &map_a, fb, k0, m0);    // 32(k) x 128(m) box
-            if (p.has_prologue) tma_load_2d(sa_lo, &map_t, fb, k0, m0);
+#pragma unroll 4
+            for (int i = ct; i < C::A_TILE / 16; i += 128) {
+              float4 hi, lo;
+              split4<false>(reinterpret_cast<float4*>(sa)[i], hi, lo);
+              reinterpret_cast<float4*>(sa_lo)[i] = lo;
+            }
           }
-          if (B_MN) {
-#pragma unroll
-            for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, fb, n0 + j * 32, k0);
+          if (p.write_hi) {
+#pragma unroll 4
+            for (int i = ct; i < C::B_TILE / 16; i += 128) {
+              float4 hi, lo;
+              split4<true>(reinterpret_cast<float4*>(sb)[i], hi, lo);
+              reinterpret_cast<float4*>(sb)[i] = hi;
+              reinterpret_cast<float4*>(sb_lo)[i] = lo;
+            }
           } else {
-            tma_load_2d(sb, &map_b, fb, k0, n0);
+#pragma unroll 4
+            for (int i = ct; i < C::B_TILE / 16; i += 128) {
+              float4 hi, lo;
+              split4<false>(reinterpret_cast<float4*>(sb)[i], hi, lo);
+              reinterpret_cast<float4*>(sb_lo)[i] = lo;
+            }
           }
+          fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(conv_bar(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
-      constexpr uint64_t adesc_base = make_smem_desc_base(A_MN);
-      constexpr uint64_t bdesc_base = make_smem_desc_base(B_MN);
-      constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;   // bytes per UMMA_K slice
-      constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1, 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kb_count; ++kb) {
-          mbar_wait(conv_bar(stage), phase, 2);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * C::STAGE;
-          const uint32_t sb = sa + C::A_TILE;
-          const uint32_t sa_lo = sb + C::B_TILE;
-          const uint32_t sb_lo = sa_lo + C::A_TILE;
-#pragma unroll
-          for (int j = 0; j < BK / UMMA_K; ++j) {
-            const uint64_t a_hi = smem_desc(adesc_base, sa + j * a_kstep);
-            const uint64_t a_lo = smem_desc(adesc_base, sa_lo + j * a_kstep);
-            const uint64_t b_hi = smem_desc(bdesc_base, sb + j * b_kstep);
-            const uint64_t b_lo = smem_desc(bdesc_base, sb_lo + j * b_kstep);
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb | j) != 0);   // small terms first
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
-          }
-          umma_commit(empty_bar(stage));                 // stage reusable once these MMAs retire
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-        }
-        umma_commit(tfull_bar(acc));                     // accumulator complete
-      }
-    }
-  } else if (warp < 6) {
-    // ===================== converters (128 threads) =====================
-    const int ct = threadIdx.x - 64;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < kb_count; ++kb) {
-        mbar_wait(full_bar(stage), phase, 3);
-        uint8_t* sa = smem_gen + stage * C::STAGE;
-        uint8_t* sb = sa + C::A_TILE;
-        uint8_t* sa_lo = sb + C::B_TILE;
-        uint8_t* sb_lo = sa_lo + C::A_TILE;
-        if (p.has_prologue) {
-#pragma unroll 4
-          for (int i = ct; i < C::A_TILE / 16; i += 128) {
-            const float4 g = reinterpret_cast<float4*>(sa)[i];
-            const float4 y = reinterpret_cast<float4*>(sa_lo)[i];
-            float4 z, hi, lo;
-            z.x = __fmul_rn(g.x, __fsub_rn(1.f, __fmul_rn(y.x, y.x)));
-            z.y = __fmul_rn(g.y, __fsub_rn(1.f, __fmul_rn(y.y, y.y)));
-            z.z = __fmul_rn(g.z, __fsub_rn(1.f, __fmul_rn(y.z, y.z)));
-            z.w = __fmul_rn(g.w, __fsub_rn(1.f, __fmul_rn(y.w, y.w)));
-            split4<true>(z, hi, lo);
-            reinterpret_cast<float4*>(sa)[i] = hi;
-            reinterpret_cast<float4*>(sa_lo)[i] = lo;
-          }
-        } else if (p.write_hi) {
-#pragma unroll 4
-          for (int i = ct; i < C::A_TILE / 16; i += 128) {
-            float4 hi, lo;
-            split4<true>(reinterpret_cast<float4*>(sa)[i], hi, lo);
-            reinterpret_cast<float4*>(sa)[i] = hi;
-            reinterpret_cast<float4*>(sa_lo)[i] = lo;
-          }
-        } else {
-#pragma unroll 4
-          for (int i = ct; i < C::A_TILE / 16; i += 128) {
-            float4 hi, lo;
-            split4<false>(reinterpret_cast<float4*>(sa)[i], hi, lo);
-            reinterpret_cast<float4*>(sa_lo)[i] = lo;
-          }
-        }
-        if (p.write_hi) {
-#pragma unroll 4
-          for (int i = ct; i < C::B_TILE / 16; i += 128) {
-            float4 hi, lo;
-            split4<true>(reinterpret_cast<float4*>(sb)[i], hi, lo);
-            reinterpret_cast<float4*>(sb)[i] = hi;
-            reinterpret_cast<float4*>(sb_lo)[i] = lo;
-          }
-        } else {
-#pragma unroll 4
-          for (int i = ct; i < C::B_TILE / 16; i += 128) {
-            float4 hi, lo;
-            split4<false>(reinterpret_cast<float4*>(sb)[i], hi, lo);
-            reinterpret_cast<float4*>(sb_lo)[i] = lo;
-          }
-        }
-        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(conv_bar(stage));
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 6..9 -> TMEM lane quadrants 2,3,0,1) =====================
-    const int quad = warp & 3;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+    // ===================== accumulate + epilogue (warps 8..15) =====================
+    reg_inc<REGS_EPILOGUE>();
+    constexpr int COLS = C::EPI_COLS;
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const int half = (warp - 8) >> 2;          // which half of the accumulator columns
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    float run[COLS];
+    uint32_t cc = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long m0 = (long long)(tile / p.n_blocks) * BM, n0 = (long long)(tile % p.n_blocks) * BN;
-      mbar_wait(tfull_bar(acc), acc_phase, 4);
-      tc_fence_after();
-      const long long row = m0 + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
-      float* crow = p.C + row * p.N;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (c == BN / 32 - 1) {           // accumulator fully read: give it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-        const long long nb = n0 + c * 32;
-        if (row < p.M && nb < p.N) {
+      for (int kb0 = 0; kb0 < kb_count; kb0 += chunk_kb, ++cc) {
+        const int acc = cc & 1;
+        mbar_wait(tfull_bar(acc), (cc >> 1) & 1, 4);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_base + acc * BN + half * COLS;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (nb + j < p.N) {           // N % 4 == 0 (checked on the host)
-              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                     __uint_as_float(r[j + 3]));
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
-              if (p.act == MT_ACT_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
-              float4* dst = reinterpret_cast<float4*>(crow + nb + j);
-              if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-              *dst = v;
+        for (int c = 0; c < COLS / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (kb0 == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) run[c * 32 + j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) run[c * 32 + j] += __uint_as_float(r[j]);   // IEEE RN fold
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));     // buffer back to the MMA warp
+      }
+      // ---- tile epilogue: bias, tanh, (accumulate), store.  One row per thread, 128 B per 32 columns.
+      const long long row = m0 + quad * 32 + lane;
+      if (row < p.M) {
+        float* crow = p.C + row * p.N;
+        const long long nb0 = n0 + half * COLS;
+#pragma unroll
+        for (int j = 0; j < COLS; j += 4) {
+          const long long n = nb0 + j;
+          if (n < p.N) {                       // N % 4 == 0 (checked on the host)
+            float4 v = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             }
+            if (p.act == MT_ACT_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+            float4* dst = reinterpret_cast<float4*>(crow + n);
+            if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
           }
         }
       }
@@ -429,7 +473,7 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D fp32 tensor map: dim0 = contiguous extent `inner`, dim1 = `outer` rows `ld` elements apart.
 static int make_map(CUtensorMap* m, const float* base, long long inner, long long outer, long long ld, int box_inner,
-                    int box_outer) {
+                    int box_outer, bool mn_major) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(MT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -437,30 +481,45 @@ static int make_map(CUtensorMap* m, const float* base, long long inner, long lon
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(MT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%dx%d", (int)r,
                 inner, outer, ld, box_inner, box_outer);
   return MT_OK;
 }
 
-static int g_write_hi = 1;   // safe default until the hardware's tf32 operand rounding is pinned
+// host-mapped word the device writes before trapping on a barrier timeout
+static int* g_dbg_host = nullptr;
+static int ensure_debug_word() {
+  if (g_dbg_host) return MT_OK;
+  MT_CUDA(cudaHostAlloc((void**)&g_dbg_host, 4 * sizeof(int), cudaHostAllocMapped));
+  memset(g_dbg_host, 0, 4 * sizeof(int));
+  int* dev = nullptr;
+  MT_CUDA(cudaHostGetDevicePointer((void**)&dev, g_dbg_host, 0));
+  MT_CUDA(cudaMemcpyToSymbol(g_dbg_word, &dev, sizeof(dev)));
+  return MT_OK;
+}
+
+// knobs (diagnostics / tuning; defaults are what the measurements in DESIGN.md chose)
+static int g_write_hi = 0;    // 0: the MMA's own truncation of the raw fp32 bits is `hi` (measured exact)
+static int g_chunk_kb = 8;    // 8 k-blocks = K 256 per TMEM accumulation chunk
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const GemmArgs& a, long long lda, long long ldb) {
   using C = Cfg<BN>;
   CUtensorMap ma, mb, mt;
   int rc;
-  if (A_MN) rc = make_map(&ma, a.A, a.M, a.K, lda, 32, BK);
-  else rc = make_map(&ma, a.A, a.K, a.M, lda, BK, BM);
+  if (A_MN) rc = make_map(&ma, a.A, a.M, a.K, lda, 32, BK, true);
+  else rc = make_map(&ma, a.A, a.K, a.M, lda, BK, BM, false);
   if (rc) return rc;
-  if (B_MN) rc = make_map(&mb, a.B, a.N, a.K, ldb, 32, BK);
-  else rc = make_map(&mb, a.B, a.K, a.N, ldb, BK, BN);
+  if (B_MN) rc = make_map(&mb, a.B, a.N, a.K, ldb, 32, BK, true);
+  else rc = make_map(&mb, a.B, a.K, a.N, ldb, BK, BN, false);
   if (rc) return rc;
   if (a.tanh_src) {
-    if (A_MN) rc = make_map(&mt, a.tanh_src, a.M, a.K, lda, 32, BK);
-    else rc = make_map(&mt, a.tanh_src, a.K, a.M, lda, BK, BM);
+    if (A_MN) rc = make_map(&mt, a.tanh_src, a.M, a.K, lda, 32, BK, true);
+    else rc = make_map(&mt, a.tanh_src, a.K, a.M, lda, BK, BM, false);
     if (rc) return rc;
   } else {
     mt = ma;
@@ -474,8 +533,11 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   p.m_blocks = (int)ceil_div(a.M, BM);
   p.n_blocks = (int)ceil_div(a.N, BN);
   p.k_blocks = (int)ceil_div(a.K, BK);
+  p.chunk_kb = g_chunk_kb > 0 ? g_chunk_kb : p.k_blocks;
   p.has_prologue = a.tanh_src ? 1 : 0;
   p.write_hi = g_write_hi;
+  rc = ensure_debug_word();
+  if (rc) return rc;
   auto kern = gemm3xtf32_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -529,9 +591,18 @@ int gemm_tc_try(const GemmArgs& a) {
 
 }  // namespace mt
 
-// diagnostic knob (tests / first hardware bring-up): 1 = converters write hi explicitly (default),
-// 0 = rely on the tensor core ignoring the low 13 mantissa bits of the raw fp32 operand.
+// diagnostic knobs (tests / hardware bring-up).
+//   write_hi : 1 = converters store a round-to-nearest hi explicitly, 0 (default) = the tensor core's own
+//              truncation of the raw fp32 operand is hi.
+//   chunk_kb : k-blocks (of 32) accumulated in TMEM between flushes into the fp32 register sums; 0 = whole K.
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_write_hi(int v) {
   tc::g_write_hi = v ? 1 : 0;
+  return MT_OK;
+}
+// after a trapped launch: {0x7100|role, block, thread, parity}; role 0 producer, 1 MMA(tempty), 2 MMA(conv),
+// 3 converter, 4 epilogue.  All zero when no wait ever timed out.
+extern "C" __attribute__((visibility("default"))) const int* mt_gemm_tc_debug_word(void) { return tc::g_dbg_host; }
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_chunk_kb(int v) {
+  tc::g_chunk_kb = v < 0 ? 0 : v;
   return MT_OK;
 }

@@ -1,0 +1,136 @@
+"""`microtorch_b200.cuda` - the array namespace `_tensor(Device.CUDA)` returns.
+
+It stands where the `cupy` module stands in the reference (src/tensor/device.py:74-84):
+the NumPy-API names the reference calls on the module object, all
+backed by libmicrotorch_b200.so.  Names that the training path never calls on CUDA and
+that the reference's own CuPy path cannot run either (where / comparisons, Q8) raise.
+"""
+
+from __future__ import annotations
+
+import numpy as _np
+
+from .. import _capi
+from . import kernels
+from .array import DeviceArray, _as_device
+
+ndarray = DeviceArray
+
+float64 = _np.float64
+float32 = _np.float32
+int64 = _np.int64
+int32 = _np.int32
+int16 = _np.int16
+int8 = _np.int8
+
+
+def is_available() -> bool:
+    """True when the shared library loads and at least one CUDA device is visible."""
+    return _capi.device_count() > 0
+
+
+def array(data, dtype=float32) -> DeviceArray:
+    if isinstance(data, DeviceArray):
+        if _np.dtype(dtype) != data.dtype:
+            return data.astype(dtype)
+        return data.copy()
+    if _np.dtype(dtype) != _np.dtype(_np.float32):
+        raise NotImplementedError(f"device arrays are float32; got dtype {_np.dtype(dtype)}")
+    return DeviceArray.from_host(data, _np.float32)
+
+
+asarray = array
+
+
+def zeros_like(x, dtype=None) -> DeviceArray:
+    return DeviceArray.zeros(x.shape)
+
+
+def ones_like(x, dtype=None) -> DeviceArray:
+    out = DeviceArray.empty(x.shape)
+    out.fill(1.0)
+    return out
+
+
+def zeros(shape, dtype=float32) -> DeviceArray:
+    return DeviceArray.zeros((shape,) if isinstance(shape, int) else shape)
+
+
+def _out(op, a, b, out):
+    if out is None:
+        return kernels.binary(op, a, b)
+    if out is a:
+        return kernels.inplace(op, out, b)
+    return kernels.binary(op, a, b, out=out)
+
+
+def add(a, b, out=None):
+    return _out(_capi.BIN_ADD, a, b, out)
+
+
+def multiply(a, b, out=None):
+    return _out(_capi.BIN_MUL, a, b, out)
+
+
+def true_divide(a, b, out=None):
+    return _out(_capi.BIN_DIV, a, b, out)
+
+
+def subtract(a, b, out=None):
+    return _out(_capi.BIN_SUB, a, b, out)
+
+
+def log(x):
+    return kernels.unary(_capi.UN_LOG, x)
+
+
+def exp(x):
+    return kernels.unary(_capi.UN_EXP, x)
+
+
+def tanh(x):
+    return kernels.unary(_capi.UN_TANH, x)
+
+
+def sum(x, axis=None, keepdims=False):      # noqa: A001
+    return kernels.sum(x, axis, keepdims)
+
+
+def transpose(x, axes=None):
+    return _as_device(x).transpose(axes)
+
+
+def squeeze(x, axis=None):
+    return _as_device(x).squeeze(axis)
+
+
+def expand_dims(x, axis):
+    return _as_device(x).expand_dims(axis)
+
+
+def broadcast_to(x, shape):
+    return _as_device(x).broadcast_to(shape)
+
+
+def outer(a, b):
+    a, b = _as_device(a), _as_device(b)
+    return kernels.binary(_capi.BIN_MUL, a.reshape((-1, 1)), b.reshape((1, -1)))
+
+
+def matmul(a, b):
+    return kernels.matmul(a, b)
+
+
+def _unsupported(name):
+    def fn(*_a, **_k):
+        raise NotImplementedError(
+            f"{name} is not implemented on the B200 backend (outside the training-step path; the "
+            "reference's CuPy path cannot run it either, SURVEY.md Q8).  There is no CPU fallback.")
+    fn.__name__ = name
+    return fn
+
+
+where = _unsupported("where")
+clip = _unsupported("clip")
+max = _unsupported("max")          # noqa: A001
+min = _unsupported("min")          # noqa: A001

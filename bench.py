@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py - MLP training-step throughput of the B200 backend (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one full training step (zero_grad, forward, loss, backward, SGD) of BASELINE.json
+config #2 - synthetic MLP 1024->4096->4096->10, Tanh + the reference's CrossEntropyLoss on
+pred*0.49+0.5, SGD, fp32 - on a per-GPU batch of 65536 rows.  N>1 is the data
+parallel trainer: every rank keeps 65536 rows (weak scaling, global batch 65536*N), weight
+gradients are all-reduced with NCCL.  Rank 0 prints ONE JSON line.
+
+  value      samples/s over all GPUs, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API with HOST inputs: every step uploads X,T from
+             pinned host memory and reads the loss back
+  roofline   the dominant kernel (tcgen05 3xTF32 GEMM): logical 2MNK flops / device time measured
+             live with CUDA events around every GEMM launch of the timed region
+  cpu_baseline / --impl reference   the oracle port of the reference's NumPy path on the host cores,
+             on a bounded sample (batch 4096) of the same workload
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+CPU_SAMPLE_BATCH = 4096
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16": d["bf16_tflops"], "bf16_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.3:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(steps=3, warmup=1):
+    """The oracle port of the reference's NumPy training step, timed on this box's host cores."""
+    from microtorch_b200 import workloads as W
+    from oracle import workloads as OW
+    from oracle.nnref import train_step
+    wl = W.scaled(W.C2, CPU_SAMPLE_BATCH)
+    model, x, t = OW.setup(wl)
+    best = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        train_step(model, x, t, wl.loss, wl.lr, wl.pred_map, wl.squeeze_dim)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            best = dt if best is None else min(best, dt)
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        blas_threads = os.cpu_count()
+    return {"value": CPU_SAMPLE_BATCH / best, "unit": "samples/s", "cores": int(blas_threads), "kind": "port",
+            "host_cpus": os.cpu_count(),
+            "sample": f"config #2 model at batch {CPU_SAMPLE_BATCH} (of 65536), best of {steps} steps after {warmup} warm-up; "
+                      "NumPy elementwise is single-threaded, only matmul uses all cores"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference
+    is pure Python and cannot travel to the GPU box), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from microtorch_b200 import workloads as W
+    from oracle import workloads as OW
+    from oracle.nnref import train_step
+    wl = W.scaled(W.C2, CPU_SAMPLE_BATCH)
+    model, x, t = OW.setup(wl)
+    for _ in range(args.warmup):
+        train_step(model, x, t, wl.loss, wl.lr, wl.pred_map, wl.squeeze_dim)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        train_step(model, x, t, wl.loss, wl.lr, wl.pred_map, wl.squeeze_dim)
+    dt = time.perf_counter() - t0
+    value = CPU_SAMPLE_BATCH * args.steps / dt
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        cores = os.cpu_count()
+    sample = f"config #2 model, batch {CPU_SAMPLE_BATCH} per step (bounded sample of 65536)"
+    print(json.dumps({
+        "impl": "reference", "metric": "mlp_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c2_mlp_1024_4096_4096_10_tanh_ce_sgd", "per_gpu_batch": 65536, "cpu_sample_batch": CPU_SAMPLE_BATCH},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": int(cores), "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
+    ap.add_argument("--batch", type=int, default=65536, help="rows per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist      # control plane only (rendezvous, barrier, max over ranks)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    from microtorch_b200 import _capi, workloads as W
+    _capi.require_device(local_rank)
+    lib = _capi.lib()
+    import microtorch_b200.nn as nn
+    from microtorch_b200.cuda import kernels as K
+    from microtorch_b200.cuda.array import DeviceArray
+    from microtorch_b200.nn.activation import Tanh
+    from microtorch_b200.nn.loss import CrossEntropyLoss, MSELoss
+    from microtorch_b200.tensor import Tensor
+    from microtorch_b200.trainer import Communicator, DataParallelTrainer
+
+    base = W.C2 if args.workload == "c2" else W.C5
+    wl = W.scaled(base, args.batch)
+    # identical replicas (same seed for the model); each rank draws its own shard of synthetic rows
+    np.random.seed(wl.seed)
+    model = W.build_model(wl, nn.Linear, Tanh, nn.Sequential)
+    rng = np.random.default_rng(1000 + rank)
+    x_host = rng.standard_normal((args.batch, wl.dims[0]), dtype=np.float32)
+    if wl.loss == "ce":
+        t_host = np.eye(wl.dims[-1], dtype=np.float32)[rng.integers(0, wl.dims[-1], args.batch)]
+    else:
+        t_host = rng.uniform(-1, 1, (args.batch, wl.dims[-1])).astype(np.float32)
+
+    comm = None
+    if world > 1:
+        def exchange(uid):
+            box = [uid]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        comm = Communicator(rank, world, exchange)
+    loss_fn = CrossEntropyLoss() if wl.loss == "ce" else MSELoss()
+    trainer = DataParallelTrainer(model, loss_fn, wl.lr, comm, wl.pred_map, wl.squeeze_dim)
+
+    def barrier():
+        _capi.check(lib.mt_sync())
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    ev0, ev1 = C.c_void_p(), C.c_void_p()
+    lib.mt_event_create(C.byref(ev0))
+    lib.mt_event_create(C.byref(ev1))
+
+    def timed(step_fn, steps):
+        barrier()
+        lib.mt_event_record(ev0)
+        for _ in range(steps):
+            step_fn()
+        lib.mt_event_record(ev1)
+        lib.mt_event_sync(ev1)
+        barrier()
+        ms = C.c_float()
+        lib.mt_event_elapsed_ms(ev0, ev1, C.byref(ms))
+        return max_over_ranks(ms.value)
+
+    # ------------------------------------------------------------- resident-input arm ("value")
+    X, T = Tensor(x_host, device="cuda"), Tensor(t_host, device="cuda")
+    last = {}
+
+    def step_resident():
+        last["loss"] = trainer.step(X, T)
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    lib.mt_prof_reset()
+    lib.mt_prof_enable(1)
+    lib.mt_launch_count_reset()
+    t_wall0 = time.time()
+    ms_total = timed(step_resident, args.steps)
+    t_wall1 = time.time()
+    launches = C.c_uint64()
+    lib.mt_launch_count(C.byref(launches))
+    n_gemm, gemm_ms, gemm_flops = C.c_uint64(), C.c_double(), C.c_double()
+    lib.mt_prof_gemm(C.byref(n_gemm), C.byref(gemm_ms), C.byref(gemm_flops))
+    lib.mt_prof_enable(0)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    loss_value = trainer.global_loss(last["loss"])
+    samples = args.batch * world * args.steps
+    value = samples / (ms_total / 1e3)
+
+    # ------------------------------------------------------------- end-to-end arm (host inputs every step)
+    hx, ht = C.c_void_p(), C.c_void_p()
+    _capi.check(lib.mt_host_alloc(C.byref(hx), x_host.nbytes))
+    _capi.check(lib.mt_host_alloc(C.byref(ht), t_host.nbytes))
+    px = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_float)), shape=x_host.shape)
+    pt = np.ctypeslib.as_array(C.cast(ht, C.POINTER(C.c_float)), shape=t_host.shape)
+    px[...] = x_host
+    pt[...] = t_host
+    e2e_loss = []
+
+    def step_e2e():
+        xs = Tensor(px, device="cuda")           # public API: H2D from pinned host memory
+        ts = Tensor(pt, device="cuda")
+        loss = trainer.step(xs, ts)
+        e2e_loss.append(loss.item())             # D2H read of the step's result
+
+    step_e2e()
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = timed(step_e2e, e2e_steps)
+    e2e_value = args.batch * world * e2e_steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    peak_tf = peaks["bf16_sustained"] / 2.0 / 3.0        # fp32-emulated (3xTF32) = TF32 dense / 3 = bf16 / 6
+    achieved_tf = (gemm_flops.value / n_gemm.value) / ((gemm_ms.value / n_gemm.value) * 1e-3) / 1e12 if n_gemm.value else 0.0
+    out = {
+        "metric": "mlp_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": ("c2_mlp_1024_4096_4096_10_tanh_ce_sgd" if args.workload == "c2" else "c5_mlp_4096x8_tanh_mse_sgd"),
+                   "per_gpu_batch": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+                   "l2": "inputs larger than L2 (activations 1 GiB per layer); no flush needed",
+                   "gemm": "tcgen05 3xTF32, chunked TMEM accumulation"},
+        "loss": loss_value,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.nbytes + t_host.nbytes) * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+        "gpu_launches": int(launches.value),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm3xtf32_kernel (tcgen05)", "achieved": achieved_tf, "peak": peak_tf,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "launches": int(n_gemm.value), "kernel_ms_per_step": gemm_ms.value / args.steps,
+                     "share_of_step": (gemm_ms.value / args.steps) / (ms_total / args.steps),
+                     "peak_source": f"{peaks['source']}: bf16 sustained {peaks['bf16_sustained']} TF/s / 2 (TF32) / 3 (3xTF32) - "
+                                    "fp32-emulated peak; burst would be %.1f" % (peaks["bf16"] / 6.0)},
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,13 @@ int mt_launch_count(uint64_t* count);
 int mt_launch_count_reset(void);
 /* overwrite a buffer larger than L2 (timing hygiene between timed iterations)           */
 int mt_l2_flush(void);
+/* per-kernel timing of the dominant kernel (bench roofline): when enabled, every tcgen05
+ * GEMM launch is bracketed by CUDA events on the compute stream; mt_prof_gemm synchronises
+ * and returns the launch count, the summed device time and the summed logical flops
+ * (2*M*N*K) since the last reset.                                                       */
+int mt_prof_enable(int on);
+int mt_prof_reset(void);
+int mt_prof_gemm(uint64_t* launches, double* ms_total, double* flops_total);
 
 /* ---------------------------------------------------------------- memory ---------- */
 /* replaces: CuPy's default MemoryPool behind every cp.array / zeros_like / operator

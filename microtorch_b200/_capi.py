@@ -40,6 +40,9 @@ PROTOTYPES = {
     "mt_launch_count": [c_u64p],
     "mt_launch_count_reset": [],
     "mt_l2_flush": [],
+    "mt_prof_enable": [C.c_int],
+    "mt_prof_reset": [],
+    "mt_prof_gemm": [c_u64p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "mt_malloc": [c_voidpp, C.c_size_t],
     "mt_free": [VP],
     "mt_pool_stats": [c_sizep, c_sizep, c_sizep, c_u64p, c_u64p],

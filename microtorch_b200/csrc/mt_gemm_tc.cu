@@ -32,6 +32,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "mt_common.cuh"
 #include "mt_gemm.cuh"
@@ -502,6 +503,18 @@ static int ensure_debug_word() {
   return MT_OK;
 }
 
+// per-launch event timing for the bench roofline (mt_prof_*)
+struct ProfRec { cudaEvent_t a, b; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
 // knobs (diagnostics / tuning; defaults are what the measurements in DESIGN.md chose)
 static int g_write_hi = 0;    // 0: the MMA's own truncation of the raw fp32 bits is `hi` (measured exact)
 static int g_chunk_kb = 8;    // 8 k-blocks = K 256 per TMEM accumulation chunk
@@ -546,7 +559,18 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   }
   const long long tiles = (long long)p.m_blocks * p.n_blocks;
   const int grid = (int)std::min<long long>(tiles, g().sm_count);
+  ProfRec rec{};
+  if (g_prof_on) {
+    rec.a = prof_event();
+    rec.b = prof_event();
+    rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
+    cudaEventRecord(rec.a, g().stream);
+  }
   kern<<<grid, NUM_THREADS, C::SMEM, g().stream>>>(ma, mb, mt, p);
+  if (g_prof_on) {
+    cudaEventRecord(rec.b, g().stream);
+    g_prof.push_back(rec);
+  }
   MT_LAUNCHED();
   return MT_OK;
 }
@@ -590,6 +614,34 @@ int gemm_tc_try(const GemmArgs& a) {
 }
 
 }  // namespace mt
+
+MT_API int mt_prof_enable(int on) {
+  tc::g_prof_on = on != 0;
+  return MT_OK;
+}
+MT_API int mt_prof_reset(void) {
+  for (auto& r : tc::g_prof) {
+    tc::g_prof_pool.push_back(r.a);
+    tc::g_prof_pool.push_back(r.b);
+  }
+  tc::g_prof.clear();
+  return MT_OK;
+}
+MT_API int mt_prof_gemm(uint64_t* launches, double* ms_total, double* flops_total) {
+  MT_REQUIRE_INIT();
+  MT_CUDA(cudaStreamSynchronize(g().stream));
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : tc::g_prof) {
+    float t = 0.f;
+    MT_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    fl += r.flops;
+  }
+  if (launches) *launches = tc::g_prof.size();
+  if (ms_total) *ms_total = ms;
+  if (flops_total) *flops_total = fl;
+  return MT_OK;
+}
 
 // diagnostic knobs (tests / hardware bring-up).
 //   write_hi : 1 = converters store a round-to-nearest hi explicitly, 0 (default) = the tensor core's own

@@ -32,6 +32,7 @@ class _Block:
     __slots__ = ("ptr", "nbytes")
 
     def __init__(self, nbytes: int) -> None:
+        self.ptr = None
         _capi.require_device()
         p = C.c_void_p()
         _capi.check(_capi.lib().mt_malloc(C.byref(p), max(int(nbytes), 1)), "mt_malloc")
@@ -39,7 +40,7 @@ class _Block:
         self.nbytes = int(nbytes)
 
     def __del__(self) -> None:
-        ptr, self.ptr = self.ptr, None
+        ptr, self.ptr = getattr(self, "ptr", None), None
         if ptr:
             try:
                 _capi.lib().mt_free(ptr)
@@ -100,8 +101,7 @@ class DeviceArray:
         scalar = None
         if isinstance(data, (int, float)) and not isinstance(data, bool):
             scalar = float(np.float32(data)) if dtype == F32 else None
-        host = np.ascontiguousarray(np.array(data, dtype=dtype, copy=False) if isinstance(data, np.ndarray)
-                                    else np.array(data, dtype=dtype))
+        host = np.ascontiguousarray(np.asarray(data, dtype=dtype))
         out = cls.empty(host.shape, dtype)
         if host.nbytes:
             _capi.check(_capi.lib().mt_h2d(out.ptr, host.ctypes.data, host.nbytes), "mt_h2d")

@@ -1,0 +1,180 @@
+"""Training-step drivers: the notebook loop as a function, and its data-parallel version.
+
+`train_step` is the reference's loop body (demo.ipynb:5178-5189): zero_grad, forward, loss,
+backward, SGD.  `DataParallelTrainer` is the new component BASELINE.json asks for (SURVEY.md
+section 8e): one process per GPU, every rank holds a full replica and a contiguous row shard
+of the batch, weight gradients are summed with NCCL over NVLink.  Each weight's all-reduce
+is queued on the communication stream the moment that weight's gradient is final (a tape
+hook), so the exchange of layer L overlaps the backward GEMMs of the layers below it; the
+fused SGD launch waits for the communication stream.  The loss is scaled by the GLOBAL
+element count, so summed rank gradients equal the single-process gradients up to fp32
+summation order and no extra 1/world pass is needed.  Bias gradients are identically zero
+(Q1) and are never exchanged.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+from . import _capi
+from .nn.loss import Loss
+from .nn.module import Module
+from .nn.optimizer import SGD
+from .tensor import Tensor
+from .tensor.device import Device
+from .tensor.tensor import _LAZY
+
+
+def train_step(model: Module, loss_fn: Loss, optimizer: SGD, x: Tensor, target: Tensor,
+               pred_map: Optional[Tuple[float, float]] = None, squeeze_dim: Optional[int] = None) -> Tensor:
+    """One step of the reference's training loop.  Returns the loss tensor (not synchronised)."""
+    model.zero_grad()
+    pred = model(x)
+    if squeeze_dim is not None:
+        pred = pred.squeeze(squeeze_dim)
+    if pred_map is not None:
+        pred = pred * pred_map[0] + pred_map[1]
+    loss = loss_fn(pred, target)
+    loss.backward()
+    optimizer.step()
+    return loss
+
+
+def shard_rows(n_rows: int, rank: int, world: int) -> slice:
+    """Contiguous row shard [r*n/W, (r+1)*n/W) of a batch (the batch must divide evenly)."""
+    if n_rows % world:
+        raise ValueError(f"global batch {n_rows} is not divisible by world size {world}")
+    per = n_rows // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+def nccl_library_path() -> Optional[str]:
+    """libnccl.so.2 shipped in the `nvidia-nccl-cu12` wheel (no torch import needed)."""
+    env = os.environ.get("MICROTORCH_B200_NCCL")
+    if env:
+        return env
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            for root in spec.submodule_search_locations:
+                cand = os.path.join(root, "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    return cand
+    except Exception:
+        pass
+    return None
+
+
+class Communicator:
+    """NCCL communicator of this process (rank r of `world`), created through the C ABI.
+
+    `exchange_id` moves the 128-byte NCCL unique id from rank 0 to everyone: any callable
+    `bytes|None -> bytes` (torch.distributed broadcast over gloo in bench.py, a file in tests)."""
+
+    def __init__(self, rank: int, world: int, exchange_id: Callable[[Optional[bytes]], bytes]) -> None:
+        self.rank, self.world = rank, world
+        self.lib = _capi.lib()
+        _capi.require_device()
+        path = nccl_library_path()
+        _capi.check(self.lib.mt_comm_load(path.encode() if path else None), "mt_comm_load")
+        uid = None
+        if rank == 0:
+            buf = C.create_string_buffer(128)
+            _capi.check(self.lib.mt_comm_unique_id(buf), "mt_comm_unique_id")
+            uid = buf.raw
+        uid = exchange_id(uid)
+        _capi.check(self.lib.mt_comm_init_rank(uid, rank, world), "mt_comm_init_rank")
+
+    def allreduce_(self, arr) -> None:
+        """In-place sum over ranks, asynchronous on the communication stream."""
+        _capi.check(self.lib.mt_allreduce_sum_f32(arr.ptr, arr.size), "mt_allreduce_sum_f32")
+
+    def wait(self) -> None:
+        _capi.check(self.lib.mt_comm_wait(), "mt_comm_wait")
+
+    def close(self) -> None:
+        self.lib.mt_comm_destroy()
+
+
+class GlooCommunicator:
+    """Same interface over torch.distributed (gloo) for Device.CPU replicas: exercises the
+    sharding / loss-scaling / hook logic of the trainer without a GPU (world_size-2 tests)."""
+
+    def __init__(self) -> None:
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def allreduce_(self, arr: np.ndarray) -> None:
+        import torch
+        t = torch.from_numpy(arr.reshape(-1))
+        self.dist.all_reduce(t)
+
+    def wait(self) -> None:
+        pass
+
+    def close(self) -> None:
+        pass
+
+
+class DataParallelTrainer:
+    def __init__(self, model: Module, loss_fn: Loss, lr: float, comm: Optional[Communicator] = None,
+                 pred_map: Optional[Tuple[float, float]] = None, squeeze_dim: Optional[int] = None) -> None:
+        self.model, self.loss_fn = model, loss_fn
+        self.comm = comm
+        self.world = comm.world if comm is not None else 1
+        self.loss_fn.world = self.world            # mean over the GLOBAL batch
+        self.optimizer = SGD(model.parameters, lr=lr)
+        self.pred_map, self.squeeze_dim = pred_map, squeeze_dim
+        self.exchanged_bytes = 0
+
+    def _on_grad_final(self, param: Tensor) -> None:
+        g = param._grad
+        if g is None or g is _LAZY:
+            return
+        if not getattr(g, "is_dense", True):
+            g = param.grad
+        if isinstance(g, np.ndarray) and not g.flags.c_contiguous:
+            g = np.ascontiguousarray(g)
+            param._grad = g
+        self.comm.allreduce_(g)
+        self.exchanged_bytes += g.nbytes
+
+    def step(self, x: Tensor, target: Tensor) -> Tensor:
+        """One data-parallel step on this rank's shard.  Returns the LOCAL partial loss (its
+        sum over ranks is the global mean loss)."""
+        model = self.model
+        model.zero_grad()
+        pred = model(x)
+        if self.squeeze_dim is not None:
+            pred = pred.squeeze(self.squeeze_dim)
+        if self.pred_map is not None:
+            pred = pred * self.pred_map[0] + self.pred_map[1]
+        loss = self.loss_fn(pred, target)
+        if self.comm is not None and self.world > 1:
+            # Parameter objects are replaced on the first forward (Q6): hook the current ones
+            for p in model.parameters():
+                p._grad_hook = self._on_grad_final
+        loss.backward()
+        if self.comm is not None and self.world > 1:
+            self.comm.wait()
+        self.optimizer.step()
+        return loss
+
+    def global_loss(self, local_loss: Tensor) -> float:
+        """Sum of the rank partial losses (host value; synchronises)."""
+        if self.comm is None or self.world == 1:
+            return float(local_loss.item())
+        if local_loss.device == Device.CPU:
+            buf = np.array(local_loss.data, dtype=np.float32).reshape((1,))
+            self.comm.allreduce_(buf)
+            return float(buf[0])
+        buf = local_loss.data.copy().reshape((1,))
+        self.comm.allreduce_(buf)
+        self.comm.wait()
+        return float(buf.get()[0])

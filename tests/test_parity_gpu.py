@@ -1,0 +1,377 @@
+"""Parity of the CUDA path (Tensor/nn API -> ctypes -> libmicrotorch_b200.so) against the oracle and
+the golden vectors made by running the reference.  Needs a B200: `-m gpu` under gpurun.
+
+The tests read like the reference's own (`Tensor(..., device="cuda")`, `.backward()`, `.to("cpu")`).
+Tolerances (north_star): index/shape ops bit-exact; elementwise + reductions 1e-5 relative;
+GEMM paths 1e-4 relative (norm-wise: |err| <= 1e-4 * max|ref|)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from microtorch_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+EW = dict(rtol=1e-5, atol=1e-7)
+
+
+@pytest.fixture(scope="module")
+def mt():
+    from microtorch_b200 import _capi
+    _capi.require_device()
+    import microtorch_b200.nn as nn
+    from microtorch_b200.nn.activation import Tanh
+    from microtorch_b200.nn.loss import BCELoss, CrossEntropyLoss, MSELoss
+    from microtorch_b200.nn.optimizer import SGD
+    from microtorch_b200.tensor import Tensor
+
+    class NS:
+        pass
+    ns = NS()
+    ns.Tensor, ns.Linear, ns.Sequential, ns.Tanh, ns.SGD = Tensor, nn.Linear, nn.Sequential, Tanh, SGD
+    ns.losses = {"mse": MSELoss, "ce": CrossEntropyLoss, "bce": BCELoss}
+    ns.lib = _capi.lib()
+    return ns
+
+
+def host(a):
+    return a.get() if hasattr(a, "get") else np.asarray(a)
+
+
+def gemm_close(got, ref, tol=1e-4):
+    got, ref = host(got).astype(np.float64), np.asarray(ref, dtype=np.float64)
+    scale = np.abs(ref).max() + 1e-30
+    assert np.abs(got - ref).max() <= tol * scale, (np.abs(got - ref).max() / scale)
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+# ----------------------------------------------------------------------------- ops vs golden + oracle
+def test_tensor_roundtrip_and_props(mt):
+    x = np.random.default_rng(0).standard_normal((5, 7)).astype(np.float32)
+    t = mt.Tensor(x, requires_grad=True, device="cuda")
+    assert t.device.value == "cuda" and t.shape == (5, 7) and t.ndim == 2 and t.size == 35
+    np.testing.assert_array_equal(host(t.data), x)
+    np.testing.assert_array_equal(host(t.grad), np.zeros_like(x))          # zero grad visible after construction
+    back = t.to("cpu")
+    np.testing.assert_array_equal(back.data, x)
+    assert mt.Tensor(3.5, device="cuda").item() == 3.5
+    with pytest.raises(ValueError):
+        t.backward()                                                        # non-scalar needs an explicit grad
+    with pytest.raises(ValueError):
+        mt.Tensor(x, device="cuda").backward()
+    with pytest.raises(ValueError):
+        t + mt.Tensor(x)                                                    # device mismatch
+
+
+def test_broadcast_poly_matches_reference_golden(mt):
+    g = load("ops_small")
+    for tag in ("same", "row", "col", "scalar", "lead", "mid", "flat"):
+        x = mt.Tensor(g[f"poly_{tag}_x"], requires_grad=True, device="cuda")
+        y = mt.Tensor(g[f"poly_{tag}_y"], requires_grad=True, device="cuda")
+        z = x * y + x ** 2 - y
+        z.sum().backward()
+        np.testing.assert_array_equal(host(z.data), g[f"poly_{tag}_z"])    # exact arithmetic: bit-exact
+        np.testing.assert_allclose(host(x.grad), g[f"poly_{tag}_gx"], **EW)
+        np.testing.assert_allclose(host(y.grad), g[f"poly_{tag}_gy"], **EW)
+        assert x.grad.shape == x.shape and y.grad.shape == y.shape
+
+
+def test_unary_pow_reductions_match_reference_golden(mt):
+    g = load("ops_small")
+    for op in ("log", "tanh", "exp"):
+        x = mt.Tensor(g["unary_x"], requires_grad=True, device="cuda")
+        r = getattr(x, op)()
+        r.sum().backward()
+        np.testing.assert_allclose(host(r.data), g[f"{op}_y"], **EW)
+        np.testing.assert_allclose(host(x.grad), g[f"{op}_gx"], **EW)
+    for p in (2, 3, -1, 0.5, 1, 0, 2.5):
+        x = mt.Tensor(g["unary_x"], requires_grad=True, device="cuda")
+        r = x ** p
+        r.sum().backward()
+        np.testing.assert_allclose(host(r.data), g[f"pow_{p}_y"], **EW)
+        np.testing.assert_allclose(host(x.grad), g[f"pow_{p}_gx"], **EW)
+    x = mt.Tensor(g["unary_x"], requires_grad=True, device="cuda")
+    m = x.mean()
+    assert m.shape == ()
+    m.backward()
+    np.testing.assert_allclose(host(m.data), g["mean_y"], **EW)
+    np.testing.assert_allclose(host(x.grad), g["mean_gx"], **EW)
+    for axis in (0, 1):
+        for keep in (0, 1):
+            x = mt.Tensor(g["unary_x"], requires_grad=True, device="cuda")
+            s = x.sum(axis=axis, keepdims=bool(keep))
+            (s * mt.Tensor(g[f"sum_a{axis}_k{keep}_w"], device="cuda")).sum().backward()
+            np.testing.assert_allclose(host(s.data), g[f"sum_a{axis}_k{keep}_y"], **EW)
+            np.testing.assert_allclose(host(x.grad), g[f"sum_a{axis}_k{keep}_gx"], **EW)
+    x = mt.Tensor(g["unary_x"], requires_grad=True, device="cuda")
+    y = mt.Tensor(g["div_y_in"], requires_grad=True, device="cuda")
+    r = (1 - x) / y + (-x)
+    r.sum().backward()
+    np.testing.assert_allclose(host(r.data), g["div_r"], **EW)
+    np.testing.assert_allclose(host(x.grad), g["div_gx"], **EW)
+    np.testing.assert_allclose(host(y.grad), g["div_gy"], **EW)
+
+
+def test_matmul_fwd_bwd_matches_reference_golden(mt):
+    g = load("ops_small")
+    a = mt.Tensor(g["mm_a"], requires_grad=True, device="cuda")
+    b = mt.Tensor(g["mm_b"], requires_grad=True, device="cuda")
+    c = a @ b
+    (c * mt.Tensor(g["mm_gw"], device="cuda")).sum().backward()
+    gemm_close(c.data, g["mm_c"])
+    gemm_close(a.grad, g["mm_ga"])
+    gemm_close(b.grad, g["mm_gb"])
+
+
+def test_index_and_shape_ops_bit_exact(mt):
+    g = load("ops_small")
+    xv = g["unary_x"]
+    x = mt.Tensor(xv, requires_grad=True, device="cuda")
+    s = x[1:4]
+    s.sum().backward()
+    np.testing.assert_array_equal(host(s.data), g["gi_slice_y"])
+    np.testing.assert_array_equal(host(x.grad), g["gi_slice_gx"])
+    x = mt.Tensor(xv, requires_grad=True, device="cuda")
+    s = x[[0, 2, 2, 4]]
+    (s * mt.Tensor(np.arange(28, dtype=np.float32).reshape(4, 7), device="cuda")).sum().backward()
+    np.testing.assert_array_equal(host(s.data), g["gi_fancy_y"])
+    np.testing.assert_array_equal(host(x.grad), g["gi_fancy_gx"])          # duplicates ASSIGN (Q10)
+    x = mt.Tensor(xv, requires_grad=True, device="cuda")
+    s = x[2, 1:5]
+    s.sum().backward()
+    np.testing.assert_array_equal(host(s.data), g["gi_tuple_y"])
+    np.testing.assert_array_equal(host(x.grad), g["gi_tuple_gx"])
+    x = mt.Tensor(g["tr_x"], requires_grad=True, device="cuda")
+    t = x.transpose((2, 0, 1))
+    (t * mt.Tensor(g["tr_gw"], device="cuda")).sum().backward()
+    np.testing.assert_array_equal(host(t.data), g["tr_y"])
+    np.testing.assert_array_equal(host(x.grad), g["tr_gx"])
+    x = mt.Tensor(g["tr_x"], requires_grad=True, device="cuda")
+    v = x.view((6, 4)).unsqueeze(1).squeeze(1).T
+    (v * mt.Tensor(g["vw_gw"], device="cuda")).sum().backward()
+    np.testing.assert_array_equal(host(v.data), g["vw_y"])
+    np.testing.assert_array_equal(host(x.grad), g["vw_gx"])
+
+
+def test_losses_match_reference_golden(mt):
+    g = load("losses_small")
+    for k, cls in mt.losses.items():
+        p = mt.Tensor(g["p"], requires_grad=True, device="cuda")
+        l = cls()(p, mt.Tensor(g["t"], device="cuda"))
+        assert l.shape == ()
+        l.backward()
+        np.testing.assert_allclose(host(l.data), g[f"{k}_loss"], rtol=1e-5)
+        np.testing.assert_allclose(host(p.grad), g[f"{k}_dp"], rtol=1e-5, atol=1e-9)
+    p = mt.Tensor(g["ce_nan_p"], requires_grad=True, device="cuda")      # tanh-range preds: NaN loss, finite grads (Q3)
+    l = mt.losses["ce"]()(p, mt.Tensor(g["t"], device="cuda"))
+    l.backward()
+    assert np.isnan(host(l.data)) and np.isnan(g["ce_nan_loss"])
+    np.testing.assert_allclose(host(p.grad), g["ce_nan_dp"], rtol=1e-5)
+    with pytest.raises(AssertionError):
+        mt.losses["mse"]()(p, mt.Tensor(np.zeros((3, 3), np.float32), device="cuda"))
+
+
+def test_composed_loss_graph_equals_fused_kernel(mt):
+    """The fused loss kernel against the same loss composed from Tensor ops on CUDA (the 6/7/13-node
+    graphs of the reference) - two independent device paths."""
+    g = load("losses_small")
+    for k, cls in mt.losses.items():
+        loss = cls()
+        p1 = mt.Tensor(g["p"], requires_grad=True, device="cuda")
+        t = mt.Tensor(g["t"], device="cuda")
+        fused = loss(p1, t)
+        fused.backward()
+        p2 = mt.Tensor(g["p"], requires_grad=True, device="cuda")
+        composed = loss.compute_loss(p2, t).mean()
+        composed.backward()
+        np.testing.assert_allclose(host(fused.data), host(composed.data), rtol=1e-5)
+        np.testing.assert_allclose(host(p1.grad), host(p2.grad), rtol=1e-5, atol=1e-9)
+
+
+# ----------------------------------------------------------------------------- training steps
+def run_cuda(mt, wl, steps, keep_first_pred=False):
+    from microtorch_b200.trainer import train_step
+    model, x, t = W.setup(wl, mt.Linear, mt.Tanh, mt.Sequential)
+    X, T = mt.Tensor(x, device="cuda"), mt.Tensor(t, device="cuda")
+    loss_fn = mt.losses[wl.loss]()
+    opt = mt.SGD(model.parameters, lr=wl.lr)
+    first = host(model(X).data) if keep_first_pred else None
+    losses, grads = [], None
+    for _ in range(steps):
+        loss = train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim)
+        losses.append(host(loss.data))
+        grads = None
+    params = list(model.parameters())
+    return {"losses": np.array(losses, np.float32), "params": [host(p.data) for p in params],
+            "grads": [host(p.grad) for p in params], "first_pred": first, "model": model}
+
+
+CASES = [
+    ("c1a_ref_120steps", W.C1A, 120),
+    ("c1b_ref_20steps", W.C1B, 20),
+    ("c2_small_3steps", W.scaled(W.C2, 96, (48, 80, 64, 10)), 3),
+    ("c4_small_2steps", W.scaled(W.C4, 4, (32, 48, 32), input_shape=(4, 6, 32)), 2),
+    ("c5_small_2steps", W.scaled(W.C5, 64, (32,) * 5), 2),
+]
+
+
+@pytest.mark.parametrize("name,wl,steps", CASES)
+def test_training_steps_match_reference_golden(mt, name, wl, steps):
+    g = load(name)
+    res = run_cuda(mt, wl, steps, keep_first_pred=True)
+    gemm_close(res["first_pred"], g["first_pred"])
+    np.testing.assert_allclose(res["losses"], g["losses"], rtol=1e-4)
+    for i, (gr, pr) in enumerate(zip(res["grads"], res["params"])):
+        gemm_close(pr, g[f"param{i}"])
+        if i % 2 == 0:
+            gemm_close(gr, g[f"grad{i}"])
+        else:                                                              # Q1: bias grad identically zero, bias unmoved
+            assert not gr.any()
+            np.testing.assert_array_equal(pr, W_initial_bias(wl, i))
+
+
+def W_initial_bias(wl, index):
+    """Bias `index` as initialised on the host (same seed, same RNG order)."""
+    from oracle import workloads as OW
+    model, _, _ = OW.setup(wl)
+    return list(model.parameters())[index].data
+
+
+def test_notebook_loss_stream_on_cuda(mt):
+    """The reference's published golden vector (demo.ipynb, CuPy run): steps 0..100 within 1e-5."""
+    pub = json.load(open(os.path.join(GOLDEN, "c1a_notebook_losses.json")))["losses"]
+    res = run_cuda(mt, W.C1A, 101)
+    want = np.array([float(pub[str(i)]) for i in range(101)], dtype=np.float32)
+    np.testing.assert_allclose(res["losses"], want, rtol=1e-5)
+
+
+def test_raw_ce_nan_loss_finite_grads_on_cuda(mt):
+    wl = W.scaled(W.C2_RAW, 96, (48, 80, 64, 10))
+    g = load("c2raw_small_1step")
+    res = run_cuda(mt, wl, 1)
+    assert np.isnan(res["losses"][0]) and np.isnan(g["losses"][0])
+    for i in range(0, len(res["grads"]), 2):
+        assert np.isfinite(res["grads"][i]).all()
+        gemm_close(res["grads"][i], g[f"grad{i}"])
+
+
+@pytest.mark.parametrize("wl,steps", [
+    (W.scaled(W.C2, 1024, (1024, 512, 256, 10)), 2),          # tcgen05 shapes + the SIMT head
+    (W.scaled(W.C5, 512, (256,) * 4), 2),
+    (W.scaled(W.C4, 8, (256, 256, 256), input_shape=(8, 64, 256)), 2),   # SURVEY 8(d) reduced 3-D case
+])
+def test_training_steps_match_oracle_at_tensor_core_sizes(mt, wl, steps):
+    """Same seeded inputs through the oracle (CPU) and the CUDA path, at sizes where the Linear GEMMs
+    run on the tcgen05 engine."""
+    from oracle import workloads as OW
+    ref = OW.run_steps(wl, steps)
+    res = run_cuda(mt, wl, steps)
+    np.testing.assert_allclose(res["losses"], ref["losses"], rtol=1e-4)
+    for i, (gr, pr) in enumerate(zip(res["grads"], res["params"])):
+        gemm_close(pr, ref["params"][i])
+        gemm_close(gr, ref["grads"][i])
+
+
+def test_unfused_linear_tanh_equals_fused_peephole(mt):
+    """Linear then Tanh called separately (4 launches, 2 tape nodes) == Sequential's fused node."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((256, 128)).astype(np.float32)
+    np.random.seed(5)
+    lin = mt.Linear(128, 192)
+    act = mt.Tanh()
+    X1 = mt.Tensor(x, requires_grad=True, device="cuda")
+    y1 = act(lin(X1))
+    y1.sum().backward()
+    gW1 = host(list(lin.parameters())[0].grad)
+    gX1 = host(X1.grad)
+    seq = mt.Sequential(lin, mt.Tanh())
+    X2 = mt.Tensor(x, requires_grad=True, device="cuda")
+    lin.zero_grad()
+    y2 = seq(X2)
+    y2.sum().backward()
+    gemm_close(y2.data, host(y1.data), 1e-5)
+    gemm_close(X2.grad, gX1, 1e-5)
+    gemm_close(list(lin.parameters())[0].grad, gW1, 1e-5)
+
+
+def test_3d_unbroadcast_reduction(mt):
+    """(h + b3) with b3 of shape (1,1,D): b3.grad is a (B*S)-row column reduction."""
+    rng = np.random.default_rng(4)
+    h = rng.standard_normal((16, 64, 256)).astype(np.float32)
+    b = rng.standard_normal((1, 1, 256)).astype(np.float32)
+    w = rng.standard_normal((16, 64, 256)).astype(np.float32)
+    H = mt.Tensor(h, requires_grad=True, device="cuda")
+    B3 = mt.Tensor(b, requires_grad=True, device="cuda")
+    ((H + B3) * mt.Tensor(w, device="cuda")).sum().backward()
+    np.testing.assert_allclose(host(B3.grad), w.astype(np.float64).sum(axis=(0, 1), keepdims=True), rtol=1e-5, atol=1e-4)
+    np.testing.assert_array_equal(host(H.grad), w)
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def test_full_size_c2_step_properties(mt):
+    """BASELINE config #2 at FULL size (B=65536): size-independent properties instead of a CPU run.
+    (1) linearity of the step in the batch: gradients of the full batch equal the sum of the gradients
+        of its two halves (each scaled to the global count) - exercises dW's K=65536 accumulation;
+    (2) Q1: bias gradients stay zero, biases unmoved;  (3) SGD: W_new == W - lr*grad exactly."""
+    from microtorch_b200.trainer import train_step
+    wl = W.C2
+    model, x, t = W.setup(wl, mt.Linear, mt.Tanh, mt.Sequential)
+    X, T = mt.Tensor(x, device="cuda"), mt.Tensor(t, device="cuda")
+    loss_fn = mt.losses["ce"]()
+
+    def grads_of(Xp, Tp, world):
+        loss_fn.world = world
+        model.zero_grad()
+        pred = model(Xp) * wl.pred_map[0] + wl.pred_map[1]
+        loss = loss_fn(pred, Tp)
+        loss.backward()
+        return float(loss.item()), [host(p.grad) for p in model.parameters()]
+
+    l_full, g_full = grads_of(X, T, 1)
+    half = wl.batch // 2
+    la, ga = grads_of(mt.Tensor(x[:half], device="cuda"), mt.Tensor(t[:half], device="cuda"), 2)
+    lb, gb = grads_of(mt.Tensor(x[half:], device="cuda"), mt.Tensor(t[half:], device="cuda"), 2)
+    assert np.isfinite(l_full)
+    assert abs((la + lb) - l_full) <= 1e-5 * abs(l_full)
+    for i, (gf, a, b) in enumerate(zip(g_full, ga, gb)):
+        if i % 2 == 0:
+            gemm_close(a + b, gf)
+        else:
+            assert not gf.any()
+    # SGD exactness on the full-size weights
+    loss_fn.world = 1
+    before = [host(p.data) for p in model.parameters()]
+    model.zero_grad()
+    pred = model(X) * wl.pred_map[0] + wl.pred_map[1]
+    loss_fn(pred, T).backward()
+    grads = [host(p.grad) for p in model.parameters()]
+    mt.SGD(model.parameters, lr=wl.lr).step()
+    after = [host(p.data) for p in model.parameters()]
+    for b0, g0, a0 in zip(before, grads, after):
+        np.testing.assert_array_equal(a0, b0 + (-(np.float32(wl.lr) * g0)))
+
+
+def test_c3_sweep_properties_large(mt):
+    """Config #3 at 2^26 elements: checks that need no CPU pass over the data -
+    sum(x) of a constant-filled tensor, linearity of sum, d/dx sum(x*y) == y, mean*N == sum."""
+    n = 1 << 26
+    x = mt.Tensor(np.full((n // 4096, 4096), 0.75, np.float32), requires_grad=True, device="cuda")
+    y_row = np.random.default_rng(6).uniform(0.5, 1.5, (1, 4096)).astype(np.float32)
+    y = mt.Tensor(y_row, requires_grad=True, device="cuda")
+    s = x.sum()
+    assert abs(s.item() - 0.75 * n) <= 1e-5 * 0.75 * n
+    z = (x * y).sum()
+    z.backward()
+    assert abs(z.item() - 0.75 * (n // 4096) * y_row.astype(np.float64).sum()) <= 1e-5 * abs(z.item())
+    gx = host(x.grad)
+    np.testing.assert_array_equal(gx[0], y_row[0])
+    np.testing.assert_array_equal(gx[-1], y_row[0])
+    np.testing.assert_allclose(host(y.grad), np.full((1, 4096), 0.75 * (n // 4096)), rtol=1e-5)
+    m = x.mean()
+    assert abs(m.item() - 0.75) <= 1e-5

@@ -101,7 +101,9 @@ class DeviceArray:
         scalar = None
         if isinstance(data, (int, float)) and not isinstance(data, bool):
             scalar = float(np.float32(data)) if dtype == F32 else None
-        host = np.ascontiguousarray(np.asarray(data, dtype=dtype))
+        host = np.asarray(data, dtype=dtype)
+        if not host.flags.c_contiguous:      # (np.ascontiguousarray would turn a 0-d scalar into shape (1,))
+            host = np.array(host, dtype=dtype, order="C")
         out = cls.empty(host.shape, dtype)
         if host.nbytes:
             _capi.check(_capi.lib().mt_h2d(out.ptr, host.ctypes.data, host.nbytes), "mt_h2d")

@@ -258,14 +258,14 @@ def test_tcgen05_engine_is_used_and_accurate(lib):
     assert eng.value == 1
     ref = np.tanh(X.astype(np.float64) @ W.astype(np.float64).T + b)
     e = gemm_err(Y.get(), ref)
-    assert e < 2e-6, e            # fp32-level, far below the 1e-4 bar
+    assert e < 2e-5, e            # fp32-level (plain TF32 would be ~1e-3), far below the 1e-4 bar
     dX, dW = Dev(shape=(M, K)), Dev(shape=(N, K))
     _capi.check(lib.mt_linear_bwd_f32(dX.ptr, dW.ptr, dYd.ptr, Y.ptr, Xd.ptr, Wd.ptr, M, N, K, 0))
     lib.mt_gemm_last_engine(C.byref(eng))
     assert eng.value == 1
     dz = dY.astype(np.float64) * (1 - Y.get().astype(np.float64) ** 2)
-    assert gemm_err(dW.get(), dz.T @ X) < 2e-6
-    assert gemm_err(dX.get(), dz @ W) < 2e-6
+    assert gemm_err(dW.get(), dz.T @ X) < 1e-5
+    assert gemm_err(dX.get(), dz @ W) < 1e-5
 
 
 def test_matmul_generic_strided_and_batched(lib):

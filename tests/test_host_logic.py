@@ -1,0 +1,100 @@
+"""CPU-only tests of the host-side logic above the C ABI (no GPU, no compute calls):
+the reduction planner, product/oracle separation, loud failure without the extension."""
+import ast
+import os
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def simulate(shape, axes):
+    """Run the [outer, red, inner] passes of plan_reduction with NumPy and return the result."""
+    from microtorch_b200.cuda.kernels import plan_reduction
+    x = np.arange(int(np.prod(shape)), dtype=np.float64).reshape(shape) if shape else np.float64(3.0).reshape(())
+    cur = x.reshape(-1)
+    for outer, red, inner in plan_reduction(shape, axes):
+        cur = cur.reshape(outer, red, inner).sum(axis=1).reshape(-1)
+    kept = [d for i, d in enumerate(shape) if i not in {a % max(len(shape), 1) for a in axes}]
+    return cur.reshape(kept), x
+
+
+@pytest.mark.parametrize("shape,axes", [((6, 8), (0,)), ((6, 8), (1,)), ((6, 8), (0, 1)), ((3, 6, 8), (0, 2)),
+                                        ((3, 6, 8), (1,)), ((2, 3, 4, 5), (0, 2)), ((2, 3, 4, 5), (1, 3)),
+                                        ((1, 7, 1), (0, 2)), ((5, 1, 7), (1,)), ((4,), (0,)), ((2, 1, 3, 1, 4), (0, 2))])
+def test_plan_reduction_matches_numpy(shape, axes):
+    got, x = simulate(shape, axes)
+    np.testing.assert_array_equal(got, x.sum(axis=tuple(axes)))
+
+
+def test_plan_reduction_merges_adjacent_axes_into_one_pass():
+    from microtorch_b200.cuda.kernels import plan_reduction
+    assert plan_reduction((256, 512, 2048), (0, 1)) == [(1, 256 * 512, 2048)]      # C4: b3.grad = one column reduction
+    assert plan_reduction((65536, 10), (0, 1)) == [(1, 655360, 1)]
+    assert plan_reduction((64, 4096), (1,)) == [(64, 4096, 1)]
+    assert plan_reduction((4, 1, 1), (1, 2)) == []
+
+
+def _imports(path):
+    tree = ast.parse(open(path).read(), path)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Import):
+            for a in node.names:
+                yield a.name
+        elif isinstance(node, ast.ImportFrom) and node.module:
+            yield ("." * node.level) + node.module
+
+
+def test_product_never_imports_the_oracle_or_torch():
+    """The oracle is test infrastructure: nothing under microtorch_b200/ may import it (or fall back
+    to torch for compute).  torch appears only in trainer.GlooCommunicator (CPU tests) and bench.py."""
+    bad = []
+    for root, _, files in os.walk(os.path.join(REPO, "microtorch_b200")):
+        for f in files:
+            if not f.endswith(".py"):
+                continue
+            path = os.path.join(root, f)
+            for mod in _imports(path):
+                top = mod.lstrip(".").split(".")[0]
+                if top == "oracle":
+                    bad.append((path, mod))
+                if top in ("torch", "cupy", "triton") and not path.endswith("trainer.py"):
+                    bad.append((path, mod))
+    assert not bad, bad
+
+
+def test_cuda_requested_without_backend_raises():
+    from microtorch_b200 import _capi
+    from microtorch_b200.tensor import Tensor
+    from microtorch_b200.tensor import device as devmod
+    if _capi.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    assert devmod.CUDA_AVAILABLE is False
+    with pytest.raises(ImportError):
+        Tensor([1.0], device="cuda")
+    with pytest.raises(ImportError):
+        devmod._device("tpu")
+    with pytest.raises(_capi.MicrotorchB200Error):          # enum bypasses the availability check, the backend does not
+        Tensor([1.0], device=devmod.Device.CUDA)
+
+
+def test_cpu_path_training_step_matches_oracle():
+    """Device.CPU of this package (NumPy backend, topological backward) against the oracle."""
+    from microtorch_b200 import workloads as W
+    import microtorch_b200.nn as nn
+    from microtorch_b200.nn.activation import Tanh
+    from microtorch_b200.nn.loss import BCELoss, CrossEntropyLoss, MSELoss
+    from microtorch_b200.nn.optimizer import SGD
+    from microtorch_b200.tensor import Tensor
+    from microtorch_b200.trainer import train_step
+    from oracle import workloads as OW
+    for wl, cls in [(W.C1A, MSELoss), (W.scaled(W.C2, 96, (48, 80, 64, 10)), CrossEntropyLoss),
+                    (W.scaled(W.C4, 4, (32, 48, 32), input_shape=(4, 6, 32)), BCELoss)]:
+        ref = OW.run_steps(wl, 3)
+        model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+        X, T, opt, loss_fn = Tensor(x), Tensor(t), SGD(model.parameters, lr=wl.lr), cls()
+        losses = [train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim).item() for _ in range(3)]
+        np.testing.assert_allclose(losses, ref["losses"], rtol=1e-5)
+        for p, want in zip(model.parameters(), ref["params"]):
+            np.testing.assert_allclose(p.data, want, rtol=1e-5, atol=1e-7)

@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""BASELINE.json config #3: broadcasting elementwise / reduction sweep through the public API,
+achieved HBM GB/s of each workload against the measured copy bandwidth (run under gpurun).
+
+Workloads, x,y ~ U(0.5,1.5) fp32, N in 2^20..2^28 (2^30 with --big):
+  poly   z = x*y + x**2 - y ; z.sum().backward()      y same-shape / (1,C) / (R,1) / scalar
+  log    x.log().sum().backward()      tanh   x.tanh().sum().backward()
+  sum    x.sum()      mean   x.mean() + backward      sum0/sum1  x.sum(axis=0/1)
+Bytes are ALGORITHMIC: the sum of the per-kernel minimum traffic of the launches
+the workload needs.  One JSON line per (workload, N); --cpu adds the oracle's time for N <= 2^24."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--min", type=int, default=20)
+    ap.add_argument("--max", type=int, default=28)
+    ap.add_argument("--step", type=int, default=2)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    from microtorch_b200 import _capi
+    _capi.require_device(0)
+    lib = _capi.lib()
+    from microtorch_b200.tensor import Tensor
+    peak = 6543.7
+    pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peak = json.load(open(pk))["hbm_gbs"]
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    lib.mt_event_create(C.byref(e0))
+    lib.mt_event_create(C.byref(e1))
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        tot = 0.0
+        for _ in range(iters):
+            lib.mt_l2_flush()
+            lib.mt_event_record(e0)
+            fn()
+            lib.mt_event_record(e1)
+            lib.mt_event_sync(e1)
+            ms = C.c_float()
+            lib.mt_event_elapsed_ms(e0, e1, C.byref(ms))
+            tot += ms.value
+        return tot / iters
+
+    rng = np.random.default_rng(0)
+    for p in range(args.min, args.max + 1, args.step):
+        n = 1 << p
+        R, Cc = n // 4096, 4096
+        xh = rng.uniform(0.5, 1.5, (R, Cc)).astype(np.float32)
+        x = Tensor(xh, requires_grad=True, device="cuda")
+        ys = {"same": rng.uniform(0.5, 1.5, (R, Cc)).astype(np.float32), "row": rng.uniform(0.5, 1.5, (1, Cc)).astype(np.float32),
+              "col": rng.uniform(0.5, 1.5, (R, 1)).astype(np.float32), "scalar": np.float32(1.25).reshape(())}
+        B = 4.0 * n
+        work = {}
+        for tag, yh in ys.items():
+            y = Tensor(yh, requires_grad=True, device="cuda")
+            m = 4.0 * yh.size
+
+            def poly(y=y):
+                x.zero_grad(); y.zero_grad()
+                z = x * y + x ** 2 - y
+                z.sum().backward()
+            # fwd: mul (2B+m), pow (2B), add (3B), neg(m) , add (2B+m) ; sum (B)
+            # bwd: x.grad = g*y [from mul] (B + m) + g*2x [pow'] (2B) accumulate (3B) ; passes for y: reduce(g*x) (B..2B), reduce(-g)
+            bytes_alg = (2 * B + m) + 2 * B + 3 * B + 2 * m + (2 * B + m) + B + (B + m + B) + 2 * B + 3 * B + (2 * B if tag == "same" else B + m) + m
+            work[f"poly_{tag}"] = (poly, bytes_alg)
+
+        def f_log():
+            x.zero_grad()
+            x.log().sum().backward()
+
+        def f_tanh():
+            x.zero_grad()
+            x.tanh().sum().backward()
+        work["log_fwd_bwd"] = (f_log, 2 * B + B + 2 * B)          # log (8N) + sum (4N) + g/x (8N: g is a broadcast scalar)
+        work["tanh_fwd_bwd"] = (f_tanh, 2 * B + B + 2 * B)
+        work["sum_fwd"] = (lambda: x.sum(), B)
+
+        def f_mean():
+            x.zero_grad()
+            x.mean().backward()
+        work["mean_fwd_bwd"] = (f_mean, B)                           # backward is a stride-0 view: no bytes until read
+        work["sum_axis0"] = (lambda: x.sum(axis=0), B)
+        work["sum_axis1"] = (lambda: x.sum(axis=1), B)
+        xd = x.data
+        from microtorch_b200.cuda import kernels as K
+        work["k_add_same"] = (lambda: K.binary(_capi.BIN_ADD, xd, xd), 3 * B)
+        work["k_tanh"] = (lambda: K.unary(_capi.UN_TANH, xd), 2 * B)
+        work["k_tanh_bwd"] = (lambda: K.binary(_capi.BIN_TANH_BWD, xd, xd), 3 * B)
+        for name, (fn, nbytes) in work.items():
+            if args.only and args.only not in name:
+                continue
+            ms = timed(fn, args.iters)
+            rec = {"workload": name, "log2_n": p, "ms": ms, "alg_gb": nbytes / 1e9, "gbs": nbytes / ms / 1e6,
+                   "frac_of_measured_hbm": nbytes / ms / 1e6 / peak}
+            print(json.dumps(rec), flush=True)
+        del x, work
+
+
+if __name__ == "__main__":
+    main()

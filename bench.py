@@ -88,8 +88,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def all_host_threads():
+    """Let BLAS use every host core (torchrun exports OMP_NUM_THREADS=1 to its children)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read+write per GEMM launch from the committed `ncu --set full` capture, or None."""
+    import csv
+    import glob
+    paths = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_gemm_ncu_full_summary.csv")))
+    if not paths:
+        return None
+    try:
+        rows = list(csv.reader(open(paths[-1])))
+        hdr = rows[0]
+        r, w = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        vals = [(float(x[r]) + float(x[w])) * 1e9 for x in rows[2:] if x and x[r]]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:
+        return None
+
+
 def cpu_baseline(steps=3, warmup=1):
     """The oracle port of the reference's NumPy training step, timed on this box's host cores."""
+    all_host_threads()
     from microtorch_b200 import workloads as W
     from oracle import workloads as OW
     from oracle.nnref import train_step
@@ -119,6 +146,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    all_host_threads()
     from microtorch_b200 import workloads as W
     from oracle import workloads as OW
     from oracle.nnref import train_step
@@ -309,7 +337,8 @@ def main():
         "gpu_launches": int(launches.value),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm3xtf32_kernel (tcgen05)", "achieved": achieved_tf, "peak": peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": ncu_traffic_per_launch(),
+                     "traffic_unit": "bytes per launch (dram read+write, ncu --set full capture under profiles/)",
                      "launches": int(n_gemm.value), "kernel_ms_per_step": gemm_ms.value / args.steps,
                      "share_of_step": (gemm_ms.value / args.steps) / (ms_total / args.steps),
                      "peak_source": f"{peaks['source']}: bf16 sustained {peaks['bf16_sustained']} TF/s / 2 (TF32) / 3 (3xTF32) - "

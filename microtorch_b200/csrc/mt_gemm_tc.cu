@@ -137,6 +137,97 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ---- cluster / CTA-pair helpers (cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int who) {
+  if (!CLUSTER) { mbar_wait(bar, parity, who); return; }
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (g_dbg_word) {
+        g_dbg_word[0] = 0x7200 | who;
+        g_dbg_word[1] = blockIdx.x;
+        g_dbg_word[2] = threadIdx.x;
+        g_dbg_word[3] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+template <int NCTA>
+__device__ __forceinline__ void tmem_alloc_n(uint32_t dst_smem, uint32_t cols) {
+  if (NCTA == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int NCTA>
+__device__ __forceinline__ void tmem_dealloc_n(uint32_t taddr, uint32_t cols) {
+  if (NCTA == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+template <int NCTA>
+__device__ __forceinline__ void umma_tf32_n(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (NCTA == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+// tcgen05.commit: 1-CTA -> own barrier; CTA pair -> the barrier at the same offset in BOTH CTAs
+template <int NCTA>
+__device__ __forceinline__ void umma_commit_n(uint32_t bar) {
+  if (NCTA == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+  }
+}
 template <int R>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 template <int R>
@@ -173,12 +264,13 @@ struct Params {
   int write_hi;       // converters store hi explicitly (else the MMA's own truncation of the raw fp32 is hi)
 };
 
-template <int BN>
+template <int BN, int NCTA>
 struct Cfg {
+  static constexpr int BN_LOCAL = BN / NCTA;            // B rows this CTA loads (CTA pair: half of N each)
   static constexpr int A_TILE = BM * BK * 4;
-  static constexpr int B_TILE = BN * BK * 4;
+  static constexpr int B_TILE = BN_LOCAL * BK * 4;
   static constexpr int STAGE = 2 * (A_TILE + B_TILE);   // raw + lo twins
-  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int STAGES = (STAGE > 65536) ? 2 : 3;
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = (NUM_ACC * BN <= 256) ? 256 : 512;
   static constexpr int EPI_COLS = BN / 2;               // accumulator columns per epilogue thread
@@ -199,11 +291,19 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   lo.w = __uint_as_float((__float_as_uint(v.w - hi.w) + 0x1000u) & 0xFFFFE000u);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// NCTA = 1: one CTA per 128 x BN tile.
+// NCTA = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile.  Each CTA holds its own 128
+//   rows of A and of the accumulator (its own TMEM) and HALF of the B tile; the leader's single MMA thread
+//   drives both tensor cores, which share the two B halves - so per SM the operand traffic out of shared
+//   memory drops by a third and a stage shrinks from 96 KB to 64 KB (3 stages instead of 2).
+//   TMA and conversion stay CTA-local; the hand-offs that cross the pair are: converters -> leader's conv[s]
+//   (remote mbarrier arrive), MMA -> both CTAs' empty[s] / tfull[a] (multicast commit), epilogues -> leader's tempty[a].
+template <int BN, bool A_MN, bool B_MN, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_t, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, NCTA>;
+  constexpr bool PAIR = (NCTA == 2);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -219,6 +319,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE + 8 * (3 * C::STAGES + 2 * NUM_ACC));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit = PAIR ? (blockIdx.x >> 1) : blockIdx.x;          // CTA (or CTA pair) index
+  const int num_units = PAIR ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
@@ -226,35 +329,36 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (p.has_prologue) prefetch_tmap(&map_t);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), 4);
+      mbar_init(conv_bar(s), 4 * NCTA);      // converter warps of every CTA of the pair
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 8 * NCTA);    // epilogue warps of every CTA of the pair
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 1) tmem_alloc_n<NCTA>(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int num_tiles = p.m_blocks * p.n_blocks;
+  const int num_tiles = p.m_blocks * p.n_blocks;       // tiles of (128*NCTA) x BN
   const int kb_count = p.k_blocks;
   const int chunk_kb = p.chunk_kb;
 
   if (warp < 8) {
     reg_dec<REGS_MOVERS>();
     if (warp == 0) {
-      // ===================== TMA producer =====================
+      // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t tx_bytes = C::A_TILE + C::B_TILE + (p.has_prologue ? C::A_TILE : 0);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-          const int m0 = (tile / p.n_blocks) * BM, n0 = (tile % p.n_blocks) * BN;
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
+          const int m0 = (tile / p.n_blocks) * (BM * NCTA) + int(cta_rank) * BM;
+          const int n0 = (tile % p.n_blocks) * BN + int(cta_rank) * C::BN_LOCAL;
           for (int kb = 0; kb < kb_count; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1, 0);
             const uint32_t sa = smem_base + stage * C::STAGE;
@@ -275,7 +379,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, fb, n0 + j * 32, k0);
+              for (int j = 0; j < C::BN_LOCAL / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, fb, n0 + j * 32, k0);
             } else {
               tma_load_2d(sb, &map_b, fb, k0, n0);
             }
@@ -284,9 +388,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       }
     } else if (warp == 1) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+      // ===================== MMA issuer (leader CTA only) =====================
+      if (lane == 0 && cta_rank == 0) {
+        constexpr uint32_t idesc = make_idesc(BM * NCTA, BN, A_MN, B_MN);
         constexpr uint64_t adesc_base = make_smem_desc_base(A_MN);
         constexpr uint64_t bdesc_base = make_smem_desc_base(B_MN);
         constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;   // bytes per UMMA_K slice
@@ -294,15 +398,15 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         uint32_t cc = 0;                                   // chunk counter across tiles -> TMEM buffer + phase
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
           for (int kb0 = 0; kb0 < kb_count; kb0 += chunk_kb, ++cc) {
             const int acc = cc & 1;
-            mbar_wait(tempty_bar(acc), ((cc >> 1) & 1) ^ 1, 1);
+            mbar_wait_t<PAIR>(tempty_bar(acc), ((cc >> 1) & 1) ^ 1, 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
             const int kb1 = min(kb0 + chunk_kb, kb_count);
             for (int kb = kb0; kb < kb1; ++kb) {
-              mbar_wait(conv_bar(stage), phase, 2);
+              mbar_wait_t<PAIR>(conv_bar(stage), phase, 2);
               tc_fence_after();
               const uint32_t sa = smem_base + stage * C::STAGE;
               const uint32_t sb = sa + C::A_TILE;
@@ -314,14 +418,14 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint64_t a_lo = smem_desc(adesc_base, sa_lo + j * a_kstep);
                 const uint64_t b_hi = smem_desc(bdesc_base, sb + j * b_kstep);
                 const uint64_t b_lo = smem_desc(bdesc_base, sb_lo + j * b_kstep);
-                umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb > kb0) || (j > 0));   // small terms first
-                umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-                umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                umma_tf32_n<NCTA>(d_tmem, a_lo, b_hi, idesc, (kb > kb0) || (j > 0));   // small terms first
+                umma_tf32_n<NCTA>(d_tmem, a_hi, b_lo, idesc, 1u);
+                umma_tf32_n<NCTA>(d_tmem, a_hi, b_hi, idesc, 1u);
               }
-              umma_commit(empty_bar(stage));               // stage reusable once these MMAs retire
+              umma_commit_n<NCTA>(empty_bar(stage));       // stage reusable (in both CTAs) once these MMAs retire
               if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(tfull_bar(acc));                   // chunk accumulator complete
+            umma_commit_n<NCTA>(tfull_bar(acc));           // chunk accumulator complete (both CTAs)
           }
         }
       }
@@ -330,7 +434,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int ct = threadIdx.x - 128;
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
         for (int kb = 0; kb < kb_count; ++kb) {
           mbar_wait(full_bar(stage), phase, 3);
           uint8_t* sa = smem_gen + stage * C::STAGE;
@@ -385,7 +489,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
           fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
-          if (lane == 0) mbar_arrive(conv_bar(stage));
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_shared(conv_bar(stage), 0));   // the LEADER's barrier
+            else mbar_arrive(conv_bar(stage));
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -399,8 +506,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
     float run[COLS];
     uint32_t cc = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long m0 = (long long)(tile / p.n_blocks) * BM, n0 = (long long)(tile % p.n_blocks) * BN;
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
+      const long long m0 = (long long)(tile / p.n_blocks) * (BM * NCTA) + (long long)cta_rank * BM;
+      const long long n0 = (long long)(tile % p.n_blocks) * BN;
       for (int kb0 = 0; kb0 < kb_count; kb0 += chunk_kb, ++cc) {
         const int acc = cc & 1;
         mbar_wait(tfull_bar(acc), (cc >> 1) & 1, 4);
@@ -421,7 +529,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));     // buffer back to the MMA warp
+        if (lane == 0) {                                   // buffer back to the (leader's) MMA warp
+          if (PAIR) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+          else mbar_arrive(tempty_bar(acc));
+        }
       }
       // ---- tile epilogue: bias, tanh, (accumulate), store.  One row per thread, 128 B per 32 columns.
       const long long row = m0 + quad * 32 + lane;
@@ -448,10 +559,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer may still touch its smem / TMEM
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    tmem_dealloc_n<NCTA>(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -519,16 +630,18 @@ static cudaEvent_t prof_event() {
 static int g_write_hi = 0;    // 0: the MMA's own truncation of the raw fp32 bits is `hi` (measured exact)
 static int g_chunk_kb = 8;    // 8 k-blocks = K 256 per TMEM accumulation chunk
 
-template <int BN, bool A_MN, bool B_MN>
+static int g_pair = 1;        // 1: CTA pairs (cta_group::2) for N > 128 when the shape allows; 0: single CTAs only
+
+template <int BN, bool A_MN, bool B_MN, int NCTA>
 static int launch(const GemmArgs& a, long long lda, long long ldb) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, NCTA>;
   CUtensorMap ma, mb, mt;
   int rc;
   if (A_MN) rc = make_map(&ma, a.A, a.M, a.K, lda, 32, BK, true);
   else rc = make_map(&ma, a.A, a.K, a.M, lda, BK, BM, false);
   if (rc) return rc;
   if (B_MN) rc = make_map(&mb, a.B, a.N, a.K, ldb, 32, BK, true);
-  else rc = make_map(&mb, a.B, a.K, a.N, ldb, BK, BN, false);
+  else rc = make_map(&mb, a.B, a.K, a.N, ldb, BK, C::BN_LOCAL, false);
   if (rc) return rc;
   if (a.tanh_src) {
     if (A_MN) rc = make_map(&mt, a.tanh_src, a.M, a.K, lda, 32, BK, true);
@@ -543,7 +656,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.act = a.act;
   p.accumulate = a.accumulate;
-  p.m_blocks = (int)ceil_div(a.M, BM);
+  p.m_blocks = (int)ceil_div(a.M, BM * NCTA);
   p.n_blocks = (int)ceil_div(a.N, BN);
   p.k_blocks = (int)ceil_div(a.K, BK);
   p.chunk_kb = g_chunk_kb > 0 ? g_chunk_kb : p.k_blocks;
@@ -551,14 +664,14 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   p.write_hi = g_write_hi;
   rc = ensure_debug_word();
   if (rc) return rc;
-  auto kern = gemm3xtf32_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm3xtf32_kernel<BN, A_MN, B_MN, NCTA>;
   static bool attr_set = false;
   if (!attr_set) {
     MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set = true;
   }
   const long long tiles = (long long)p.m_blocks * p.n_blocks;
-  const int grid = (int)std::min<long long>(tiles, g().sm_count);
+  const int units = (int)std::min<long long>(tiles, g().sm_count / NCTA);
   ProfRec rec{};
   if (g_prof_on) {
     rec.a = prof_event();
@@ -566,21 +679,34 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
     rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
     cudaEventRecord(rec.a, g().stream);
   }
-  kern<<<grid, NUM_THREADS, C::SMEM, g().stream>>>(ma, mb, mt, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(units * NCTA));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.stream = g().stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, mt, p);
   if (g_prof_on) {
     cudaEventRecord(rec.b, g().stream);
     g_prof.push_back(rec);
   }
+  if (le != cudaSuccess) return fail(MT_ERR_CUDA, "gemm3xtf32 launch failed: %s", cudaGetErrorString(le));
   MT_LAUNCHED();
   return MT_OK;
 }
 
-template <int BN>
+template <int BN, int NCTA>
 static int dispatch_major(const GemmArgs& a, bool a_mn, bool b_mn, long long lda, long long ldb) {
-  if (!a_mn && !b_mn) return launch<BN, false, false>(a, lda, ldb);
-  if (!a_mn && b_mn) return launch<BN, false, true>(a, lda, ldb);
-  if (a_mn && !b_mn) return launch<BN, true, false>(a, lda, ldb);
-  return launch<BN, true, true>(a, lda, ldb);
+  if (!a_mn && !b_mn) return launch<BN, false, false, NCTA>(a, lda, ldb);
+  if (!a_mn && b_mn) return launch<BN, false, true, NCTA>(a, lda, ldb);
+  if (a_mn && !b_mn) return launch<BN, true, false, NCTA>(a, lda, ldb);
+  return launch<BN, true, true, NCTA>(a, lda, ldb);
 }
 
 }  // namespace tc
@@ -609,8 +735,10 @@ int gemm_tc_try(const GemmArgs& a) {
     return MT_ERR_UNSUPPORTED;
   }
   if (ceil_div(a.M, tc::BM) * ceil_div(a.N, 128) > 0x7fffffffLL) return MT_ERR_UNSUPPORTED;
-  const bool wide = a.N > 128;
-  return wide ? tc::dispatch_major<256>(a, a_mn, b_mn, lda, ldb) : tc::dispatch_major<128>(a, a_mn, b_mn, lda, ldb);
+  if (a.N <= 128) return tc::dispatch_major<128, 1>(a, a_mn, b_mn, lda, ldb);
+  // CTA pairs need enough 256-row tiles to keep 74 pairs busy; small M stays on single CTAs
+  const bool pair = tc::g_pair && a.M >= 256;
+  return pair ? tc::dispatch_major<256, 2>(a, a_mn, b_mn, lda, ldb) : tc::dispatch_major<256, 1>(a, a_mn, b_mn, lda, ldb);
 }
 
 }  // namespace mt
@@ -654,6 +782,11 @@ extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_write_hi(in
 // after a trapped launch: {0x7100|role, block, thread, parity}; role 0 producer, 1 MMA(tempty), 2 MMA(conv),
 // 3 converter, 4 epilogue.  All zero when no wait ever timed out.
 extern "C" __attribute__((visibility("default"))) const int* mt_gemm_tc_debug_word(void) { return tc::g_dbg_host; }
+//   pair     : 1 (default) = CTA pairs (tcgen05 cta_group::2) for wide problems, 0 = single-CTA tiles only.
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_pair(int v) {
+  tc::g_pair = v ? 1 : 0;
+  return MT_OK;
+}
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_chunk_kb(int v) {
   tc::g_chunk_kb = v < 0 ? 0 : v;
   return MT_OK;

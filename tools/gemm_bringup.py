@@ -16,32 +16,31 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 
 # name, M, N, K (Linear convention: X[M,K], W[N,K], Y[M,N]), kind, write_hi, chunk_kb, timing
 CASES = [
-    ("fwd_small", 256, 256, 64, "fwd", 0, 8, 0),
-    ("fwd_small_hi", 256, 256, 64, "fwd", 1, 8, 0),
-    ("fwd_bias_tanh", 384, 512, 160, "fwd_act", 0, 8, 0),
-    ("fwd_ragged", 200, 132, 100, "fwd", 0, 8, 0),
-    ("fwd_n128", 512, 128, 256, "fwd", 0, 8, 0),
-    ("fwd_chunks", 256, 256, 1024, "fwd", 0, 4, 0),
-    ("dx_small", 256, 256, 128, "dx", 0, 8, 0),
-    ("dx_prologue", 256, 256, 128, "dx_pro", 0, 8, 0),
-    ("dw_small", 256, 256, 256, "dw", 0, 8, 0),
-    ("dw_prologue_acc", 512, 256, 384, "dw_pro_acc", 0, 8, 0),
-    ("dw_ragged", 300, 132, 100, "dw_pro", 0, 8, 0),
-    ("fwd_4096_c8", 8192, 4096, 4096, "fwd_act", 0, 8, 1),
-    ("fwd_4096_c0", 8192, 4096, 4096, "fwd_act", 0, 0, 1),
-    ("fwd_4096_c16", 8192, 4096, 4096, "fwd_act", 0, 16, 1),
-    ("fwd_4096_hi", 8192, 4096, 4096, "fwd_act", 1, 8, 1),
-    ("dx_4096", 8192, 4096, 4096, "dx_pro", 0, 8, 1),
-    ("dw_4096", 8192, 4096, 4096, "dw_pro", 0, 8, 1),
-    ("fwd_c2_l1", 65536, 4096, 1024, "fwd_act", 0, 8, 1),
-    ("fwd_c2_l2", 65536, 4096, 4096, "fwd_act", 0, 8, 1),
-    ("dx_c2_l2", 65536, 4096, 4096, "dx_pro", 0, 8, 1),
-    ("dw_c2_l2", 65536, 4096, 4096, "dw_pro", 0, 8, 1),
-    ("dw_c2_l1", 65536, 4096, 1024, "dw_pro", 0, 8, 1),
+    # name, M, N, K, kind, write_hi, chunk_kb, timing, pair
+    ("fwd_small", 256, 256, 64, "fwd", 0, 8, 0, 1),
+    ("fwd_small_1cta", 256, 256, 64, "fwd", 0, 8, 0, 0),
+    ("fwd_bias_tanh", 384, 512, 160, "fwd_act", 0, 8, 0, 1),
+    ("fwd_ragged", 300, 132, 100, "fwd", 0, 8, 0, 1),
+    ("fwd_n128", 512, 128, 256, "fwd", 0, 8, 0, 1),
+    ("fwd_chunks", 512, 256, 1024, "fwd", 0, 4, 0, 1),
+    ("dx_small", 256, 256, 128, "dx", 0, 8, 0, 1),
+    ("dx_prologue", 512, 256, 128, "dx_pro", 0, 8, 0, 1),
+    ("dw_small", 256, 256, 256, "dw", 0, 8, 0, 1),
+    ("dw_prologue_acc", 512, 256, 384, "dw_pro_acc", 0, 8, 0, 1),
+    ("dw_ragged", 300, 260, 420, "dw_pro", 0, 8, 0, 1),
+    ("fwd_4096_pair", 8192, 4096, 4096, "fwd_act", 0, 8, 1, 1),
+    ("fwd_4096_1cta", 8192, 4096, 4096, "fwd_act", 0, 8, 1, 0),
+    ("fwd_c2_l1_pair", 65536, 4096, 1024, "fwd_act", 0, 8, 1, 1),
+    ("fwd_c2_l2_pair", 65536, 4096, 4096, "fwd_act", 0, 8, 1, 1),
+    ("fwd_c2_l2_1cta", 65536, 4096, 4096, "fwd_act", 0, 8, 1, 0),
+    ("dx_c2_l2_pair", 65536, 4096, 4096, "dx_pro", 0, 8, 1, 1),
+    ("dw_c2_l2_pair", 65536, 4096, 4096, "dw_pro", 0, 8, 1, 1),
+    ("dw_c2_l2_1cta", 65536, 4096, 4096, "dw_pro", 0, 8, 1, 0),
+    ("dw_c2_l1_pair", 65536, 4096, 1024, "dw_pro", 0, 8, 1, 1),
 ]
 
 
-def run_case(name, M, N, K, kind, write_hi, chunk_kb, timing):
+def run_case(name, M, N, K, kind, write_hi, chunk_kb, timing, pair):
     import ctypes as C
     import numpy as np
     from microtorch_b200 import _capi
@@ -52,6 +51,8 @@ def run_case(name, M, N, K, kind, write_hi, chunk_kb, timing):
     lib.mt_gemm_tc_set_chunk_kb.argtypes = [C.c_int]
     lib.mt_gemm_tc_set_write_hi(write_hi)
     lib.mt_gemm_tc_set_chunk_kb(chunk_kb)
+    lib.mt_gemm_tc_set_pair.argtypes = [C.c_int]
+    lib.mt_gemm_tc_set_pair(pair)
     rng = np.random.default_rng(1)
     X = rng.standard_normal((M, K), dtype=np.float32)
     W = (rng.standard_normal((N, K), dtype=np.float32) * 0.05).astype(np.float32)
@@ -99,7 +100,7 @@ def run_case(name, M, N, K, kind, write_hi, chunk_kb, timing):
         _capi.check(rc, "mt_linear_bwd_f32")
         return dX if (kind.startswith("dx") and want_dx) else dW
 
-    res = {"case": name, "M": M, "N": N, "K": K, "kind": kind, "write_hi": write_hi, "chunk_kb": chunk_kb}
+    res = {"case": name, "M": M, "N": N, "K": K, "kind": kind, "write_hi": write_hi, "chunk_kb": chunk_kb, "pair": pair}
     out_tc = call(1)
     _capi.check(lib.mt_sync(), "sync")
     eng = C.c_int(-2)
@@ -140,7 +141,17 @@ def run_case(name, M, N, K, kind, write_hi, chunk_kb, timing):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--case":
         c = [x for x in CASES if x[0] == sys.argv[2]][0]
-        run_case(*c)
+        try:
+            run_case(*c)
+        except Exception as e:           # after a device trap: report which barrier wait timed out
+            import ctypes as C
+            from microtorch_b200 import _capi
+            lib = _capi.lib()
+            lib.mt_gemm_tc_debug_word.restype = C.POINTER(C.c_int)
+            w = lib.mt_gemm_tc_debug_word()
+            words = [hex(w[i]) for i in range(4)] if w else None
+            print("RESULT " + json.dumps({"case": c[0], "error": str(e)[-300:], "debug_word": words}), flush=True)
+            sys.exit(1)
         sys.exit(0)
     only = sys.argv[1:] or None
     for c in CASES:
@@ -153,7 +164,7 @@ if __name__ == "__main__":
             if lines:
                 print(lines[-1][7:], flush=True)
             else:
-                print(json.dumps({"case": c[0], "rc": r.returncode, "stdout": r.stdout[-600:], "stderr": r.stderr[-1200:]}),
+                print(json.dumps({"case": c[0], "rc": r.returncode, "stdout": r.stdout[-600:], "stderr": r.stderr[-1500:]}),
                       flush=True)
         except subprocess.TimeoutExpired:
             print(json.dumps({"case": c[0], "error": "timeout"}), flush=True)

@@ -262,18 +262,32 @@ struct Params {
   int chunk_kb;       // k-blocks accumulated in TMEM before a flush to the fp32 register sums
   int has_prologue;   // A' = A * (1 - T^2)
   int write_hi;       // converters store hi explicitly (else the MMA's own truncation of the raw fp32 is hi)
+  int dbg;            // timing experiments only (results are wrong): 1 skip the conversion, 2 issue hi*hi only,
+                      // 4 issue no MMA at all
 };
 
-template <int BN, int NCTA>
+// Shared-memory plan.  Two rings with different lifetimes:
+//   raw ring : TMA destination [A | B | (Y tile for the tanh' prologue)], alive from the TMA issue until the MMAs
+//              that read it retire - deep (up to 5 stages), because the TMA round trip (~1.2-2.4 us measured,
+//              profiles/r01_gemm_pipeline_experiments.jsonl) is longer than one k-block of tensor work (~0.85 us);
+//   lo ring  : converter output [A_lo | B_lo], alive from the conversion until the same MMAs retire - 2 stages,
+//              enough for the conversion of k-block i+1 to overlap the MMAs of k-block i.
+template <int BN, int NCTA, bool PRO>
 struct Cfg {
   static constexpr int BN_LOCAL = BN / NCTA;            // B rows this CTA loads (CTA pair: half of N each)
   static constexpr int A_TILE = BM * BK * 4;
   static constexpr int B_TILE = BN_LOCAL * BK * 4;
-  static constexpr int STAGE = 2 * (A_TILE + B_TILE);   // raw + lo twins
-  static constexpr int STAGES = (STAGE > 65536) ? 2 : 3;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int RAW_STAGE = A_TILE + B_TILE + (PRO ? A_TILE : 0);
+  static constexpr int LO_STAGE = A_TILE + B_TILE;
+  static constexpr int LO_STAGES = 2;
+  static constexpr int SMEM_MAX = 232448;               // 227 KB opt-in limit per CTA
+  static constexpr int AUX = 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int RAW_FIT = (SMEM_MAX - AUX - LO_STAGES * LO_STAGE) / RAW_STAGE;
+  static constexpr int RAW_STAGES = RAW_FIT > 6 ? 6 : RAW_FIT;
+  static constexpr int SMEM = RAW_STAGES * RAW_STAGE + LO_STAGES * LO_STAGE + AUX;
   static constexpr int TMEM_COLS = (NUM_ACC * BN <= 256) ? 256 : 512;
   static constexpr int EPI_COLS = BN / 2;               // accumulator columns per epilogue thread
+  static_assert(RAW_STAGES >= 2, "raw ring too shallow");
 };
 
 // hi/lo split of one 16-byte vector.  RN=true rounds hi to nearest tf32 (needs the explicit hi store);
@@ -298,25 +312,29 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 //   memory drops by a third and a stage shrinks from 96 KB to 64 KB (3 stages instead of 2).
 //   TMA and conversion stay CTA-local; the hand-offs that cross the pair are: converters -> leader's conv[s]
 //   (remote mbarrier arrive), MMA -> both CTAs' empty[s] / tfull[a] (multicast commit), epilogues -> leader's tempty[a].
-template <int BN, bool A_MN, bool B_MN, int NCTA>
+template <int BN, bool A_MN, bool B_MN, int NCTA, bool PRO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_t, const Params p) {
-  using C = Cfg<BN, NCTA>;
+  using C = Cfg<BN, NCTA, PRO>;
+  constexpr int R = C::RAW_STAGES, L = C::LO_STAGES;
   constexpr bool PAIR = (NCTA == 2);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // barrier block after the stages
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto conv_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * C::STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * C::STAGES + NUM_ACC + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (3 * C::STAGES + 2 * NUM_ACC);
+  // layout: [raw ring][lo ring][barriers]
+  const uint32_t lo_base = smem_base + R * C::RAW_STAGE;
+  const uint32_t bar_base = lo_base + L * C::LO_STAGE;
+  auto full_bar = [&](int r) { return bar_base + 8u * r; };                 // raw stage r: TMA bytes landed
+  auto empty_bar = [&](int r) { return bar_base + 8u * (R + r); };          // raw stage r: MMAs retired
+  auto conv_bar = [&](int l) { return bar_base + 8u * (2 * R + l); };       // lo stage l: k-block converted
+  auto lofree_bar = [&](int l) { return bar_base + 8u * (2 * R + L + l); }; // lo stage l: MMAs retired
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * R + 2 * L + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * R + 2 * L + NUM_ACC + a); };
+  constexpr int kSlot = 8 * (2 * R + 2 * L + 2 * NUM_ACC);
+  const uint32_t tmem_slot = bar_base + kSlot;
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE + 8 * (3 * C::STAGES + 2 * NUM_ACC));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + R * C::RAW_STAGE + L * C::LO_STAGE + kSlot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
@@ -326,11 +344,14 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
-    if (p.has_prologue) prefetch_tmap(&map_t);
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(conv_bar(s), 4 * NCTA);      // converter warps of every CTA of the pair
-      mbar_init(empty_bar(s), 1);
+    if (PRO) prefetch_tmap(&map_t);
+    for (int r = 0; r < R; ++r) {
+      mbar_init(full_bar(r), 1);
+      mbar_init(empty_bar(r), 1);
+    }
+    for (int l = 0; l < L; ++l) {
+      mbar_init(conv_bar(l), 4 * NCTA);      // converter warps of every CTA of the pair
+      mbar_init(lofree_bar(l), 1);
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -355,15 +376,15 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx_bytes = C::A_TILE + C::B_TILE + (p.has_prologue ? C::A_TILE : 0);
+        const uint32_t tx_bytes = C::RAW_STAGE;
         for (int tile = unit; tile < num_tiles; tile += num_units) {
           const int m0 = (tile / p.n_blocks) * (BM * NCTA) + int(cta_rank) * BM;
           const int n0 = (tile % p.n_blocks) * BN + int(cta_rank) * C::BN_LOCAL;
           for (int kb = 0; kb < kb_count; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1, 0);
-            const uint32_t sa = smem_base + stage * C::STAGE;
+            const uint32_t sa = smem_base + stage * C::RAW_STAGE;
             const uint32_t sb = sa + C::A_TILE;
-            const uint32_t sa_lo = sb + C::B_TILE;
+            const uint32_t sa_lo = sb + C::B_TILE;        // prologue only: the Y tile rides in the raw stage
             const uint32_t fb = full_bar(stage);
             mbar_expect_tx(fb, tx_bytes);
             const int k0 = kb * BK;
@@ -371,11 +392,11 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
               for (int j = 0; j < BM / 32; ++j) {   // 32(m) x 32(k) boxes, 4096 B each
                 tma_load_2d(sa + j * 4096, &map_a, fb, m0 + j * 32, k0);
-                if (p.has_prologue) tma_load_2d(sa_lo + j * 4096, &map_t, fb, m0 + j * 32, k0);
+                if (PRO) tma_load_2d(sa_lo + j * 4096, &map_t, fb, m0 + j * 32, k0);
               }
             } else {
               tma_load_2d(sa, &map_a, fb, k0, m0);    // 32(k) x 128(m) box
-              if (p.has_prologue) tma_load_2d(sa_lo, &map_t, fb, k0, m0);
+              if (PRO) tma_load_2d(sa_lo, &map_t, fb, k0, m0);
             }
             if (B_MN) {
 #pragma unroll
@@ -383,7 +404,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             } else {
               tma_load_2d(sb, &map_b, fb, k0, n0);
             }
-            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == R) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -395,8 +416,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         constexpr uint64_t bdesc_base = make_smem_desc_base(B_MN);
         constexpr uint32_t a_kstep = A_MN ? 1024u : 32u;   // bytes per UMMA_K slice
         constexpr uint32_t b_kstep = B_MN ? 1024u : 32u;
-        int stage = 0;
-        uint32_t phase = 0;
+        int stage = 0, lo = 0;
+        uint32_t lphase = 0;
         uint32_t cc = 0;                                   // chunk counter across tiles -> TMEM buffer + phase
         for (int tile = unit; tile < num_tiles; tile += num_units) {
           for (int kb0 = 0; kb0 < kb_count; kb0 += chunk_kb, ++cc) {
@@ -406,11 +427,11 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t d_tmem = tmem_base + acc * BN;
             const int kb1 = min(kb0 + chunk_kb, kb_count);
             for (int kb = kb0; kb < kb1; ++kb) {
-              mbar_wait_t<PAIR>(conv_bar(stage), phase, 2);
+              mbar_wait_t<PAIR>(conv_bar(lo), lphase, 2);
               tc_fence_after();
-              const uint32_t sa = smem_base + stage * C::STAGE;
+              const uint32_t sa = smem_base + stage * C::RAW_STAGE;
               const uint32_t sb = sa + C::A_TILE;
-              const uint32_t sa_lo = sb + C::B_TILE;
+              const uint32_t sa_lo = lo_base + lo * C::LO_STAGE;
               const uint32_t sb_lo = sa_lo + C::A_TILE;
 #pragma unroll
               for (int j = 0; j < BK / UMMA_K; ++j) {
@@ -418,12 +439,18 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint64_t a_lo = smem_desc(adesc_base, sa_lo + j * a_kstep);
                 const uint64_t b_hi = smem_desc(bdesc_base, sb + j * b_kstep);
                 const uint64_t b_lo = smem_desc(bdesc_base, sb_lo + j * b_kstep);
+                if (p.dbg & 6) {                                                       // timing experiments
+                  if (p.dbg & 2) umma_tf32_n<NCTA>(d_tmem, a_hi, b_hi, idesc, (kb > kb0) || (j > 0));
+                  continue;
+                }
                 umma_tf32_n<NCTA>(d_tmem, a_lo, b_hi, idesc, (kb > kb0) || (j > 0));   // small terms first
                 umma_tf32_n<NCTA>(d_tmem, a_hi, b_lo, idesc, 1u);
                 umma_tf32_n<NCTA>(d_tmem, a_hi, b_hi, idesc, 1u);
               }
-              umma_commit_n<NCTA>(empty_bar(stage));       // stage reusable (in both CTAs) once these MMAs retire
-              if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+              umma_commit_n<NCTA>(empty_bar(stage));       // both rings' slots reusable (in both CTAs) once these
+              umma_commit_n<NCTA>(lofree_bar(lo));         // MMAs retire
+              if (++stage == R) stage = 0;
+              if (++lo == L) { lo = 0; lphase ^= 1; }
             }
             umma_commit_n<NCTA>(tfull_bar(acc));           // chunk accumulator complete (both CTAs)
           }
@@ -432,20 +459,24 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     } else if (warp >= 4) {
       // ===================== converters (warps 4..7, 128 threads) =====================
       const int ct = threadIdx.x - 128;
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, lo = 0;
+      uint32_t phase = 0, lphase = 0;
       for (int tile = unit; tile < num_tiles; tile += num_units) {
         for (int kb = 0; kb < kb_count; ++kb) {
-          mbar_wait(full_bar(stage), phase, 3);
-          uint8_t* sa = smem_gen + stage * C::STAGE;
+          mbar_wait(lofree_bar(lo), lphase ^ 1, 5);          // lo slot free (usually long since)
+          mbar_wait(full_bar(stage), phase, 3);              // raw bytes landed
+          uint8_t* sa = smem_gen + stage * C::RAW_STAGE;
           uint8_t* sb = sa + C::A_TILE;
-          uint8_t* sa_lo = sb + C::B_TILE;
+          uint8_t* sy = sb + C::B_TILE;                      // prologue only: Y tile
+          uint8_t* sa_lo = smem_gen + R * C::RAW_STAGE + lo * C::LO_STAGE;
           uint8_t* sb_lo = sa_lo + C::A_TILE;
-          if (p.has_prologue) {
+          if (p.dbg & 1) {
+            // timing experiment: hand the stage over untouched
+          } else if (PRO) {
 #pragma unroll 4
             for (int i = ct; i < C::A_TILE / 16; i += 128) {
               const float4 g = reinterpret_cast<float4*>(sa)[i];
-              const float4 y = reinterpret_cast<float4*>(sa_lo)[i];
+              const float4 y = reinterpret_cast<float4*>(sy)[i];
               float4 z, hi, lo;
               z.x = __fmul_rn(g.x, __fsub_rn(1.f, __fmul_rn(y.x, y.x)));
               z.y = __fmul_rn(g.y, __fsub_rn(1.f, __fmul_rn(y.y, y.y)));
@@ -471,7 +502,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               reinterpret_cast<float4*>(sa_lo)[i] = lo;
             }
           }
-          if (p.write_hi) {
+          if (p.dbg & 1) {
+          } else if (p.write_hi) {
 #pragma unroll 4
             for (int i = ct; i < C::B_TILE / 16; i += 128) {
               float4 hi, lo;
@@ -490,10 +522,11 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(mapa_shared(conv_bar(stage), 0));   // the LEADER's barrier
-            else mbar_arrive(conv_bar(stage));
+            if (PAIR) mbar_arrive_cluster(mapa_shared(conv_bar(lo), 0));      // the LEADER's barrier
+            else mbar_arrive(conv_bar(lo));
           }
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == R) { stage = 0; phase ^= 1; }
+          if (++lo == L) { lo = 0; lphase ^= 1; }
         }
       }
     }
@@ -630,11 +663,12 @@ static cudaEvent_t prof_event() {
 static int g_write_hi = 0;    // 0: the MMA's own truncation of the raw fp32 bits is `hi` (measured exact)
 static int g_chunk_kb = 8;    // 8 k-blocks = K 256 per TMEM accumulation chunk
 
+static int g_dbg_flags = 0;   // Params::dbg
 static int g_pair = 1;        // 1: CTA pairs (cta_group::2) for N > 128 when the shape allows; 0: single CTAs only
 
-template <int BN, bool A_MN, bool B_MN, int NCTA>
+template <int BN, bool A_MN, bool B_MN, int NCTA, bool PRO>
 static int launch(const GemmArgs& a, long long lda, long long ldb) {
-  using C = Cfg<BN, NCTA>;
+  using C = Cfg<BN, NCTA, PRO>;
   CUtensorMap ma, mb, mt;
   int rc;
   if (A_MN) rc = make_map(&ma, a.A, a.M, a.K, lda, 32, BK, true);
@@ -662,9 +696,10 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   p.chunk_kb = g_chunk_kb > 0 ? g_chunk_kb : p.k_blocks;
   p.has_prologue = a.tanh_src ? 1 : 0;
   p.write_hi = g_write_hi;
+  p.dbg = g_dbg_flags;
   rc = ensure_debug_word();
   if (rc) return rc;
-  auto kern = gemm3xtf32_kernel<BN, A_MN, B_MN, NCTA>;
+  auto kern = gemm3xtf32_kernel<BN, A_MN, B_MN, NCTA, PRO>;
   static bool attr_set = false;
   if (!attr_set) {
     MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -701,12 +736,17 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   return MT_OK;
 }
 
+template <int BN, int NCTA, bool PRO>
+static int dispatch_major2(const GemmArgs& a, bool a_mn, bool b_mn, long long lda, long long ldb) {
+  if (!a_mn && !b_mn) return launch<BN, false, false, NCTA, PRO>(a, lda, ldb);
+  if (!a_mn && b_mn) return launch<BN, false, true, NCTA, PRO>(a, lda, ldb);
+  if (a_mn && !b_mn) return launch<BN, true, false, NCTA, PRO>(a, lda, ldb);
+  return launch<BN, true, true, NCTA, PRO>(a, lda, ldb);
+}
 template <int BN, int NCTA>
 static int dispatch_major(const GemmArgs& a, bool a_mn, bool b_mn, long long lda, long long ldb) {
-  if (!a_mn && !b_mn) return launch<BN, false, false, NCTA>(a, lda, ldb);
-  if (!a_mn && b_mn) return launch<BN, false, true, NCTA>(a, lda, ldb);
-  if (a_mn && !b_mn) return launch<BN, true, false, NCTA>(a, lda, ldb);
-  return launch<BN, true, true, NCTA>(a, lda, ldb);
+  return a.tanh_src ? dispatch_major2<BN, NCTA, true>(a, a_mn, b_mn, lda, ldb)
+                    : dispatch_major2<BN, NCTA, false>(a, a_mn, b_mn, lda, ldb);
 }
 
 }  // namespace tc
@@ -783,6 +823,10 @@ extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_write_hi(in
 // 3 converter, 4 epilogue.  All zero when no wait ever timed out.
 extern "C" __attribute__((visibility("default"))) const int* mt_gemm_tc_debug_word(void) { return tc::g_dbg_host; }
 //   pair     : 1 (default) = CTA pairs (tcgen05 cta_group::2) for wide problems, 0 = single-CTA tiles only.
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_dbg(int v) {
+  tc::g_dbg_flags = v;
+  return MT_OK;
+}
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_pair(int v) {
   tc::g_pair = v ? 1 : 0;
   return MT_OK;

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Timing experiments on the tcgen05 GEMM (run under gpurun): which stage bounds the pipeline?
+Flags: 1 = converters skip their work, 2 = only the hi*hi MMA is issued, 4 = no MMA issued.
+Results with flags != 0 are numerically wrong on purpose; only the time matters."""
+import ctypes as C
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np  # noqa: E402
+from microtorch_b200 import _capi  # noqa: E402
+from capi_util import Dev  # noqa: E402
+
+lib = _capi.lib()
+_capi.require_device(0)
+for f in ("mt_gemm_tc_set_dbg", "mt_gemm_tc_set_pair", "mt_gemm_tc_set_chunk_kb"):
+    getattr(lib, f).argtypes = [C.c_int]
+M, N, K = 65536, 4096, 4096
+rng = np.random.default_rng(0)
+X = Dev(rng.standard_normal((M, K), dtype=np.float32))
+W = Dev((rng.standard_normal((N, K), dtype=np.float32) * 0.05).astype(np.float32))
+dY = Dev(rng.standard_normal((M, N), dtype=np.float32))
+Y = Dev(shape=(M, N))
+dW = Dev(shape=(N, K))
+dX = Dev(shape=(M, K))
+lib.mt_gemm_set_engine(1)
+e0, e1 = C.c_void_p(), C.c_void_p()
+lib.mt_event_create(C.byref(e0))
+lib.mt_event_create(C.byref(e1))
+
+
+def time_it(fn, iters=4):
+    fn()
+    ts = []
+    for _ in range(iters):
+        lib.mt_event_record(e0)
+        fn()
+        lib.mt_event_record(e1)
+        lib.mt_event_sync(e1)
+        ms = C.c_float()
+        lib.mt_event_elapsed_ms(e0, e1, C.byref(ms))
+        ts.append(ms.value)
+    return min(ts), sorted(ts)[len(ts) // 2]
+
+
+def fwd():
+    _capi.check(lib.mt_linear_fwd_f32(Y.ptr, X.ptr, W.ptr, None, M, N, K, 0))
+
+
+def dw():
+    _capi.check(lib.mt_linear_bwd_f32(None, dW.ptr, dY.ptr, None, X.ptr, W.ptr, M, N, K, 0))
+
+
+flops = 2.0 * M * N * K
+for pair in (1, 0):
+    for chunk in (8, 0):
+        for dbg in (0, 1, 2, 3, 4, 5):
+            if chunk == 0 and dbg not in (0, 4):
+                continue
+            lib.mt_gemm_tc_set_pair(pair)
+            lib.mt_gemm_tc_set_chunk_kb(chunk)
+            lib.mt_gemm_tc_set_dbg(dbg)
+            for name, fn in (("fwd", fwd), ("dw", dw)):
+                mn, med = time_it(fn)
+                print(json.dumps({"op": name, "pair": pair, "chunk_kb": chunk, "dbg": dbg, "ms_min": mn, "ms_med": med,
+                                  "tflops_logical_at_min": flops / mn / 1e9}), flush=True)

@@ -152,13 +152,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id) does: the cluster-scope release
+  // compiles to MEMBAR.ALL.GPU in front of every arrive and showed up as a ~1.7 us converter<->MMA round trip
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -262,6 +264,7 @@ struct Params {
   int chunk_kb;       // k-blocks accumulated in TMEM before a flush to the fp32 register sums
   int has_prologue;   // A' = A * (1 - T^2)
   int write_hi;       // converters store hi explicitly (else the MMA's own truncation of the raw fp32 is hi)
+  int raw_stages, lo_stages;   // ring depths (runtime: the split of the 227 KB is a tuning knob)
   int dbg;            // timing experiments only (results are wrong): 1 skip the conversion, 2 issue hi*hi only,
                       // 4 issue no MMA at all
 };
@@ -279,15 +282,12 @@ struct Cfg {
   static constexpr int B_TILE = BN_LOCAL * BK * 4;
   static constexpr int RAW_STAGE = A_TILE + B_TILE + (PRO ? A_TILE : 0);
   static constexpr int LO_STAGE = A_TILE + B_TILE;
-  static constexpr int LO_STAGES = 2;
   static constexpr int SMEM_MAX = 232448;               // 227 KB opt-in limit per CTA
-  static constexpr int AUX = 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int RAW_FIT = (SMEM_MAX - AUX - LO_STAGES * LO_STAGE) / RAW_STAGE;
-  static constexpr int RAW_STAGES = RAW_FIT > 6 ? 6 : RAW_FIT;
-  static constexpr int SMEM = RAW_STAGES * RAW_STAGE + LO_STAGES * LO_STAGE + AUX;
+  static constexpr int MAX_STAGES = 8;                  // per ring (barrier arrays are sized for this)
+  static constexpr int AUX = 1024 /*align slack*/ + 512 /*barriers*/;
   static constexpr int TMEM_COLS = (NUM_ACC * BN <= 256) ? 256 : 512;
   static constexpr int EPI_COLS = BN / 2;               // accumulator columns per epilogue thread
-  static_assert(RAW_STAGES >= 2, "raw ring too shallow");
+  static int smem_bytes(int r, int l) { return r * RAW_STAGE + l * LO_STAGE + AUX; }
 };
 
 // hi/lo split of one 16-byte vector.  RN=true rounds hi to nearest tf32 (needs the explicit hi store);
@@ -374,7 +374,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_t, const Params p) {
   using C = Cfg<BN, NCTA, PRO>;
-  constexpr int R = C::RAW_STAGES, L = C::LO_STAGES;
+  constexpr int MS = C::MAX_STAGES;
+  const int R = p.raw_stages, L = p.lo_stages;
   constexpr bool PAIR = (NCTA == 2);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -383,12 +384,12 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t lo_base = smem_base + R * C::RAW_STAGE;
   const uint32_t bar_base = lo_base + L * C::LO_STAGE;
   auto full_bar = [&](int r) { return bar_base + 8u * r; };                 // raw stage r: TMA bytes landed
-  auto empty_bar = [&](int r) { return bar_base + 8u * (R + r); };          // raw stage r: MMAs retired
-  auto conv_bar = [&](int l) { return bar_base + 8u * (2 * R + l); };       // lo stage l: k-block converted
-  auto lofree_bar = [&](int l) { return bar_base + 8u * (2 * R + L + l); }; // lo stage l: MMAs retired
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * R + 2 * L + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * R + 2 * L + NUM_ACC + a); };
-  constexpr int kSlot = 8 * (2 * R + 2 * L + 2 * NUM_ACC);
+  auto empty_bar = [&](int r) { return bar_base + 8u * (MS + r); };         // raw stage r: MMAs retired
+  auto conv_bar = [&](int l) { return bar_base + 8u * (2 * MS + l); };      // lo stage l: k-block converted
+  auto lofree_bar = [&](int l) { return bar_base + 8u * (3 * MS + l); };    // lo stage l: MMAs retired
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (4 * MS + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (4 * MS + NUM_ACC + a); };
+  constexpr int kSlot = 8 * (4 * MS + 2 * NUM_ACC);
   const uint32_t tmem_slot = bar_base + kSlot;
   volatile uint32_t* tmem_slot_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + R * C::RAW_STAGE + L * C::LO_STAGE + kSlot);
@@ -681,6 +682,8 @@ static int g_write_hi = 0;    // 0: the MMA's own truncation of the raw fp32 bit
 static int g_chunk_kb = 8;    // 8 k-blocks = K 256 per TMEM accumulation chunk
 
 static int g_dbg_flags = 0;   // Params::dbg
+static int g_lo_stages = 3;   // lo ring depth; the raw ring gets whatever else fits (or g_raw_stages if > 0)
+static int g_raw_stages = 0;
 static int g_pair = 1;        // 1: CTA pairs (cta_group::2) for N > 128 when the shape allows; 0: single CTAs only
 
 template <int BN, bool A_MN, bool B_MN, int NCTA, bool PRO>
@@ -714,12 +717,26 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   p.has_prologue = a.tanh_src ? 1 : 0;
   p.write_hi = g_write_hi;
   p.dbg = g_dbg_flags;
+  {  // ring depths: lo ring g_lo_stages deep (default 3), raw ring takes the rest of the 227 KB
+    int l = g_lo_stages, r = g_raw_stages;
+    const int room = C::SMEM_MAX - C::AUX;
+    if (l < 1) l = 1;
+    if (l > C::MAX_STAGES) l = C::MAX_STAGES;
+    while (l > 1 && room - l * C::LO_STAGE < 2 * C::RAW_STAGE) --l;
+    const int fit = (room - l * C::LO_STAGE) / C::RAW_STAGE;
+    if (r <= 0 || r > fit) r = fit;
+    if (r > C::MAX_STAGES) r = C::MAX_STAGES;
+    if (r < 1) return fail(MT_ERR_INVALID, "gemm3xtf32: no room for a raw stage");
+    p.raw_stages = r;
+    p.lo_stages = l;
+  }
+  const int smem_bytes = C::smem_bytes(p.raw_stages, p.lo_stages);
   rc = ensure_debug_word();
   if (rc) return rc;
   auto kern = gemm3xtf32_kernel<BN, A_MN, B_MN, NCTA, PRO>;
   static bool attr_set = false;
   if (!attr_set) {
-    MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_MAX));
     attr_set = true;
   }
   const long long tiles = (long long)p.m_blocks * p.n_blocks;
@@ -734,7 +751,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(units * NCTA));
   cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = C::SMEM;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = g().stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -840,6 +857,11 @@ extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_write_hi(in
 // 3 converter, 4 epilogue.  All zero when no wait ever timed out.
 extern "C" __attribute__((visibility("default"))) const int* mt_gemm_tc_debug_word(void) { return tc::g_dbg_host; }
 //   pair     : 1 (default) = CTA pairs (tcgen05 cta_group::2) for wide problems, 0 = single-CTA tiles only.
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_rings(int raw_stages, int lo_stages) {
+  tc::g_raw_stages = raw_stages;
+  tc::g_lo_stages = lo_stages;
+  return MT_OK;
+}
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_dbg(int v) {
   tc::g_dbg_flags = v;
   return MT_OK;

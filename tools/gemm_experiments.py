@@ -54,15 +54,28 @@ def dw():
 
 
 flops = 2.0 * M * N * K
-for pair in (1, 0):
-    for chunk in (8, 0):
+lib.mt_gemm_tc_set_rings.argtypes = [C.c_int, C.c_int]
+mode = sys.argv[1] if len(sys.argv) > 1 else "rings"
+if mode == "rings":
+    # ring-depth sweep: (raw, lo); raw=0 -> whatever fits
+    for pair, rings in ((1, [(0, 2), (0, 3), (0, 4), (3, 3), (2, 5)]), (0, [(0, 1), (0, 2)])):
+        for raw, lo in rings:
+            for dbg in (0, 4, 5):
+                lib.mt_gemm_tc_set_pair(pair)
+                lib.mt_gemm_tc_set_chunk_kb(8)
+                lib.mt_gemm_tc_set_rings(raw, lo)
+                lib.mt_gemm_tc_set_dbg(dbg)
+                for name, fn in (("fwd", fwd), ("dw", dw)):
+                    mn, med = time_it(fn)
+                    print(json.dumps({"op": name, "pair": pair, "raw": raw, "lo": lo, "dbg": dbg, "ms_min": mn, "ms_med": med,
+                                      "tflops_logical_at_min": flops / mn / 1e9}), flush=True)
+else:
+    for pair in (1, 0):
         for dbg in (0, 1, 2, 3, 4, 5):
-            if chunk == 0 and dbg not in (0, 4):
-                continue
             lib.mt_gemm_tc_set_pair(pair)
-            lib.mt_gemm_tc_set_chunk_kb(chunk)
+            lib.mt_gemm_tc_set_chunk_kb(8)
             lib.mt_gemm_tc_set_dbg(dbg)
             for name, fn in (("fwd", fwd), ("dw", dw)):
                 mn, med = time_it(fn)
-                print(json.dumps({"op": name, "pair": pair, "chunk_kb": chunk, "dbg": dbg, "ms_min": mn, "ms_med": med,
+                print(json.dumps({"op": name, "pair": pair, "dbg": dbg, "ms_min": mn, "ms_med": med,
                                   "tflops_logical_at_min": flops / mn / 1e9}), flush=True)

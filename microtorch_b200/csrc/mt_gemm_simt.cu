@@ -148,6 +148,19 @@ int launch(const GemmArgs& a, long long batch) {
 
 namespace mt {
 
+int splitk_finalize(float* C, const float* partial, int splits, long long M, long long N, const float* bias, int act,
+                    int accumulate) {
+  float* sum = nullptr;
+  int rc = pool_alloc((void**)&sum, sizeof(float) * (size_t)M * N);
+  if (rc) return rc;
+  rc = mt_reduce_sum_f32(sum, partial, 1, splits, M * N, nullptr, 0, 0, 0);
+  if (rc) return rc;
+  splitk_epilogue_kernel<<<ew_grid(M * N, 1024), 256, 0, g().stream>>>(C, sum, bias, M, N, act, accumulate);
+  MT_LAUNCHED();
+  pool_free(sum);
+  return MT_OK;
+}
+
 int gemm_simt(GemmArgs a, long long batch) {
   if (a.M == 0 || a.N == 0 || batch == 0) return MT_OK;
   MT_CHECK_ARG(batch <= 65535, "matmul: batch %lld exceeds 65535", batch);
@@ -182,16 +195,9 @@ int gemm_simt(GemmArgs a, long long batch) {
   else rc = launch<16, 256, 4, 4>(a, batch);
   if (rc) return rc;
   if (splits > 1) {
-    float* sum = nullptr;
-    rc = pool_alloc((void**)&sum, sizeof(float) * a.M * a.N);
-    if (rc) return rc;
-    rc = mt_reduce_sum_f32(sum, partial, 1, splits, a.M * a.N, nullptr, 0, 0, 0);
-    if (rc) return rc;
-    splitk_epilogue_kernel<<<ew_grid(a.M * a.N, 1024), 256, 0, g().stream>>>(final_c, sum, a.bias, a.M, a.N, a.act,
-                                                                            a.accumulate);
-    MT_LAUNCHED();
-    pool_free(sum);
+    rc = splitk_finalize(final_c, partial, (int)splits, a.M, a.N, a.bias, a.act, a.accumulate);
     pool_free(partial);
+    if (rc) return rc;
   }
   return MT_OK;
 }

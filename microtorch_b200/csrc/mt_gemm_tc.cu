@@ -264,6 +264,8 @@ struct Params {
   int chunk_kb;       // k-blocks accumulated in TMEM before a flush to the fp32 register sums
   int has_prologue;   // A' = A * (1 - T^2)
   int write_hi;       // converters store hi explicitly (else the MMA's own truncation of the raw fp32 is hi)
+  int splits, kb_per_split;    // split-K: work item = (tile, split); split s covers k-blocks [s*kbps, (s+1)*kbps)
+                               // and writes its partial to C + s*M*N (folded by splitk_finalize)
   int raw_stages, lo_stages;   // ring depths (runtime: the split of the 227 KB is a tuning knob)
   int dbg;            // timing experiments only (results are wrong): 1 skip the conversion, 2 issue hi*hi only,
                       // 4 issue no MMA at all
@@ -423,9 +425,12 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int num_tiles = p.m_blocks * p.n_blocks;       // tiles of (128*NCTA) x BN
-  const int kb_count = p.k_blocks;
+  const int num_work = p.m_blocks * p.n_blocks * p.splits;   // (tile of (128*NCTA) x BN, k-split) pairs
   const int chunk_kb = p.chunk_kb;
+  // work item w -> tile index, k-block range
+  auto work_tile = [&](int w) { return w / p.splits; };
+  auto work_kb0 = [&](int w) { return (w % p.splits) * p.kb_per_split; };
+  auto work_kb1 = [&](int w) { return min(((w % p.splits) + 1) * p.kb_per_split, p.k_blocks); };
 
   if (warp < 8) {
     reg_dec<REGS_MOVERS>();
@@ -435,10 +440,11 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t tx_bytes = C::RAW_STAGE;
-        for (int tile = unit; tile < num_tiles; tile += num_units) {
+        for (int w = unit; w < num_work; w += num_units) {
+          const int tile = work_tile(w);
           const int m0 = (tile / p.n_blocks) * (BM * NCTA) + int(cta_rank) * BM;
           const int n0 = (tile % p.n_blocks) * BN + int(cta_rank) * C::BN_LOCAL;
-          for (int kb = 0; kb < kb_count; ++kb) {
+          for (int kb = work_kb0(w), kbe = work_kb1(w); kb < kbe; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1, 0);
             const uint32_t sa = smem_base + stage * C::RAW_STAGE;
             const uint32_t sb = sa + C::A_TILE;
@@ -477,13 +483,14 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int stage = 0, lo = 0;
         uint32_t lphase = 0;
         uint32_t cc = 0;                                   // chunk counter across tiles -> TMEM buffer + phase
-        for (int tile = unit; tile < num_tiles; tile += num_units) {
-          for (int kb0 = 0; kb0 < kb_count; kb0 += chunk_kb, ++cc) {
+        for (int w = unit; w < num_work; w += num_units) {
+          const int kb_end = work_kb1(w);
+          for (int kb0 = work_kb0(w); kb0 < kb_end; kb0 += chunk_kb, ++cc) {
             const int acc = cc & 1;
             mbar_wait_t<PAIR>(tempty_bar(acc), ((cc >> 1) & 1) ^ 1, 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
-            const int kb1 = min(kb0 + chunk_kb, kb_count);
+            const int kb1 = min(kb0 + chunk_kb, kb_end);
             for (int kb = kb0; kb < kb1; ++kb) {
               mbar_wait_t<PAIR>(conv_bar(lo), lphase, 2);
               tc_fence_after();
@@ -519,8 +526,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int ct = threadIdx.x - 128;
       int stage = 0, lo = 0;
       uint32_t phase = 0, lphase = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
-        for (int kb = 0; kb < kb_count; ++kb) {
+      for (int w = unit; w < num_work; w += num_units) {
+        for (int kb = work_kb0(w), kbe = work_kb1(w); kb < kbe; ++kb) {
           mbar_wait(lofree_bar(lo), lphase ^ 1, 5);          // lo slot free (usually long since)
           mbar_wait(full_bar(stage), phase, 3);              // raw bytes landed
           uint8_t* sa = smem_gen + stage * C::RAW_STAGE;
@@ -557,10 +564,12 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint32_t lane_base = uint32_t(quad * 32) << 16;
     float run[COLS];
     uint32_t cc = 0;
-    for (int tile = unit; tile < num_tiles; tile += num_units) {
+    for (int w = unit; w < num_work; w += num_units) {
+      const int tile = work_tile(w);
       const long long m0 = (long long)(tile / p.n_blocks) * (BM * NCTA) + (long long)cta_rank * BM;
       const long long n0 = (long long)(tile % p.n_blocks) * BN;
-      for (int kb0 = 0; kb0 < kb_count; kb0 += chunk_kb, ++cc) {
+      const int kb_begin = work_kb0(w), kb_end = work_kb1(w);
+      for (int kb0 = kb_begin; kb0 < kb_end; kb0 += chunk_kb, ++cc) {
         const int acc = cc & 1;
         mbar_wait(tfull_bar(acc), (cc >> 1) & 1, 4);
         tc_fence_after();
@@ -570,7 +579,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
-          if (kb0 == 0) {
+          if (kb0 == kb_begin) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) run[c * 32 + j] = __uint_as_float(r[j]);
           } else {
@@ -588,7 +597,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // ---- tile epilogue: bias, tanh, (accumulate), store.  One row per thread, 128 B per 32 columns.
       const long long row = m0 + quad * 32 + lane;
       if (row < p.M) {
-        float* crow = p.C + row * p.N;
+        float* crow = p.C + (long long)(w % p.splits) * p.M * p.N + row * p.N;   // split partials are stacked
         const long long nb0 = n0 + half * COLS;
 #pragma unroll
         for (int j = 0; j < COLS; j += 4) {
@@ -682,6 +691,7 @@ static int g_write_hi = 0;    // 0: the MMA's own truncation of the raw fp32 bit
 static int g_chunk_kb = 8;    // 8 k-blocks = K 256 per TMEM accumulation chunk
 
 static int g_dbg_flags = 0;   // Params::dbg
+static int g_splitk = 1;      // allow split-K for badly quantised tile counts
 static int g_lo_stages = 3;   // lo ring depth; the raw ring gets whatever else fits (or g_raw_stages if > 0)
 static int g_raw_stages = 0;
 static int g_pair = 1;        // 1: CTA pairs (cta_group::2) for N > 128 when the shape allows; 0: single CTAs only
@@ -730,6 +740,32 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
     p.raw_stages = r;
     p.lo_stages = l;
   }
+  // split-K when the tile count quantises badly over the 148/NCTA persistent units (dW: 256 tiles on 74 pairs = 4
+  // waves at 86 %): pick the smallest S <= 8 whose wave efficiency reaches 95 %, keeping >= 64 k-blocks per split
+  const long long tiles = (long long)p.m_blocks * p.n_blocks;
+  const long long unit_count = g().sm_count / NCTA;
+  int S = 1;
+  if (g_splitk && tiles < 8 * unit_count) {
+    double best = 0.0;
+    for (int s = 1; s <= 8; ++s) {
+      if (s > 1 && p.k_blocks / s < 64) break;
+      const long long work = tiles * s;
+      const double eff = (double)work / (double)(ceil_div(work, unit_count) * unit_count);
+      if (eff > best + 0.02) { best = eff; S = s; }
+      if (best >= 0.95) break;
+    }
+  }
+  p.kb_per_split = (int)ceil_div(p.k_blocks, S);
+  p.splits = (int)ceil_div(p.k_blocks, p.kb_per_split);
+  float* partial = nullptr;
+  if (p.splits > 1) {
+    rc = pool_alloc((void**)&partial, sizeof(float) * (size_t)p.splits * a.M * a.N);
+    if (rc) return rc;
+    p.C = partial;
+    p.bias = nullptr;
+    p.act = MT_ACT_NONE;
+    p.accumulate = 0;
+  }
   const int smem_bytes = C::smem_bytes(p.raw_stages, p.lo_stages);
   rc = ensure_debug_word();
   if (rc) return rc;
@@ -739,8 +775,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
     MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_MAX));
     attr_set = true;
   }
-  const long long tiles = (long long)p.m_blocks * p.n_blocks;
-  const int units = (int)std::min<long long>(tiles, g().sm_count / NCTA);
+  const int units = (int)std::min<long long>(tiles * p.splits, unit_count);
   ProfRec rec{};
   if (g_prof_on) {
     rec.a = prof_event();
@@ -767,6 +802,11 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   }
   if (le != cudaSuccess) return fail(MT_ERR_CUDA, "gemm3xtf32 launch failed: %s", cudaGetErrorString(le));
   MT_LAUNCHED();
+  if (partial) {
+    rc = splitk_finalize(a.C, partial, p.splits, a.M, a.N, a.bias, a.act, a.accumulate);
+    pool_free(partial);
+    if (rc) return rc;
+  }
   return MT_OK;
 }
 
@@ -860,6 +900,10 @@ extern "C" __attribute__((visibility("default"))) const int* mt_gemm_tc_debug_wo
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_rings(int raw_stages, int lo_stages) {
   tc::g_raw_stages = raw_stages;
   tc::g_lo_stages = lo_stages;
+  return MT_OK;
+}
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_splitk(int v) {
+  tc::g_splitk = v ? 1 : 0;
   return MT_OK;
 }
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_dbg(int v) {

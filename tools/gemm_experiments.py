@@ -56,6 +56,31 @@ def dw():
 flops = 2.0 * M * N * K
 lib.mt_gemm_tc_set_rings.argtypes = [C.c_int, C.c_int]
 mode = sys.argv[1] if len(sys.argv) > 1 else "rings"
+lib.mt_gemm_tc_set_splitk.argtypes = [C.c_int]
+Yact = Dev(np.tanh(rng.standard_normal((M, N), dtype=np.float32)).astype(np.float32))
+
+
+def dw_pro():
+    _capi.check(lib.mt_linear_bwd_f32(None, dW.ptr, dY.ptr, Yact.ptr, X.ptr, W.ptr, M, N, K, 0))
+
+
+def bwd_pro():   # dW + dX, both with the fused tanh' prologue
+    _capi.check(lib.mt_linear_bwd_f32(dX.ptr, dW.ptr, dY.ptr, Yact.ptr, X.ptr, W.ptr, M, N, K, 0))
+
+
+if mode == "final":
+    lib.mt_gemm_tc_set_pair(1)
+    lib.mt_gemm_tc_set_chunk_kb(8)
+    lib.mt_gemm_tc_set_dbg(0)
+    for splitk in (1, 0):
+        for raw, lo in ((0, 2), (0, 3)):
+            lib.mt_gemm_tc_set_splitk(splitk)
+            lib.mt_gemm_tc_set_rings(raw, lo)
+            for name, fn, nf in (("fwd", fwd, 1), ("dw", dw, 1), ("dw_pro", dw_pro, 1), ("dw_pro+dx_pro", bwd_pro, 2)):
+                mn, med = time_it(fn)
+                print(json.dumps({"op": name, "splitk": splitk, "raw": raw, "lo": lo, "ms_min": mn, "ms_med": med,
+                                  "tflops_logical_at_min": nf * flops / mn / 1e9}), flush=True)
+    sys.exit(0)
 if mode == "rings":
     # ring-depth sweep: (raw, lo); raw=0 -> whatever fits
     for pair, rings in ((1, [(0, 2), (0, 3), (0, 4), (3, 3), (2, 5)]), (0, [(0, 1), (0, 2)])):

@@ -167,9 +167,12 @@ int mt_linear_fwd_f32(float* Y, const float* X, const float* W, const float* bia
  * dW[N,K] (+)= dZ^T . X ;  dX[M,K] = dZ . W   (dX skipped when NULL).  No bias gradient:
  * the reference's bias is outside the tape (linear.py:61-62, tensor.py:547-550; Q1).
  * replaces: matmul.bkwd_a / bkwd_b (overload.py:137-154) and tanh backward (math.py:74) */
+#define MT_LINEAR_ACCUMULATE_DW 1            /* dW += instead of dW =                                        */
+#define MT_LINEAR_DX_TIMES_TANH_GRAD_OF_X 2 /* dX <- dX * (1 - X^2): X is itself a tanh output, so the dX    */
+                                            /* epilogue emits the PRODUCING layer's pre-activation gradient  */
+                                            /* (its dZ) and that layer then runs plain GEMMs (Yact = NULL)    */
 int mt_linear_bwd_f32(float* dX_or_null, float* dW, const float* dY, const float* Yact_or_null,
-                      const float* X, const float* W, int64_t M, int64_t N, int64_t K,
-                      int accumulate_dW);
+                      const float* X, const float* W, int64_t M, int64_t N, int64_t K, int flags);
 /* generic C[b] = A[b] @ B[b] for the bare `@` (overload.py:132,142,153): element strides
  * for every operand, batch stride 0 broadcasts.  C is row-major [batch, M, N].          */
 int mt_matmul_f32(float* C, const float* A, const float* B, int64_t batch, int64_t M, int64_t N,

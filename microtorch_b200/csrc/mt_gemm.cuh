@@ -17,6 +17,8 @@ struct GemmArgs {
   long long a_sb, a_sm, a_sk, b_sb, b_sk, b_sn;
   const float* bias;      // [N] or NULL
   const float* tanh_src;  // same layout as A, or NULL
+  const float* epi_tanh;  // [M,N] like C, or NULL: C = result * (1 - epi_tanh^2)  (emit the producer's pre-activation
+                          // gradient straight from the dX epilogue: tanh' fused into the PRODUCER instead of a prologue)
   int act;                // mt_act
   int accumulate;         // C += result
   // SIMT split-K bookkeeping (filled by gemm_simt)
@@ -27,7 +29,7 @@ struct GemmArgs {
 int gemm_simt(GemmArgs a, long long batch);
 // C = act(sum_s partial[s] + bias) (+ C): deterministic fold of split-K partials stacked as [splits, M, N]
 int splitk_finalize(float* C, const float* partial, int splits, long long M, long long N, const float* bias, int act,
-                    int accumulate);
+                    int accumulate, const float* epi_tanh);
 // MT_OK if the tcgen05 engine ran it, MT_ERR_UNSUPPORTED if the layout/shape is not one it
 // takes (caller falls back to SIMT), anything else is a real error.
 int gemm_tc_try(const GemmArgs& a);

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(THREADS) sgemm_kernel(const GemmArgs p) {
       if (p.splits == 1) {
         if (p.bias) v += __ldg(p.bias + gn);
         if (p.act == MT_ACT_TANH) v = tanhf(v);
+        if (p.epi_tanh) { const float t = __ldg(p.epi_tanh + gm * p.N + gn); v = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(t, t))); }
         if (p.accumulate) v += C[gm * p.N + gn];
       }
       C[gm * p.N + gn] = v;
@@ -124,13 +125,14 @@ __global__ void __launch_bounds__(THREADS) sgemm_kernel(const GemmArgs p) {
 // epilogue of a split-K run: C = act(sum + bias) (+ C)
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(float* __restrict__ C, const float* __restrict__ sum,
                                                               const float* __restrict__ bias, long long M, long long N,
-                                                              int act, int accumulate) {
+                                                              int act, int accumulate, const float* __restrict__ epi_tanh) {
   const long long total = M * N;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     float v = sum[i];
     if (bias) v += __ldg(bias + i % N);
     if (act == MT_ACT_TANH) v = tanhf(v);
+    if (epi_tanh) { const float t = __ldg(epi_tanh + i); v = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(t, t))); }
     if (accumulate) v += C[i];
     C[i] = v;
   }
@@ -149,13 +151,13 @@ int launch(const GemmArgs& a, long long batch) {
 namespace mt {
 
 int splitk_finalize(float* C, const float* partial, int splits, long long M, long long N, const float* bias, int act,
-                    int accumulate) {
+                    int accumulate, const float* epi_tanh) {
   float* sum = nullptr;
   int rc = pool_alloc((void**)&sum, sizeof(float) * (size_t)M * N);
   if (rc) return rc;
   rc = mt_reduce_sum_f32(sum, partial, 1, splits, M * N, nullptr, 0, 0, 0);
   if (rc) return rc;
-  splitk_epilogue_kernel<<<ew_grid(M * N, 1024), 256, 0, g().stream>>>(C, sum, bias, M, N, act, accumulate);
+  splitk_epilogue_kernel<<<ew_grid(M * N, 1024), 256, 0, g().stream>>>(C, sum, bias, M, N, act, accumulate, epi_tanh);
   MT_LAUNCHED();
   pool_free(sum);
   return MT_OK;
@@ -195,7 +197,7 @@ int gemm_simt(GemmArgs a, long long batch) {
   else rc = launch<16, 256, 4, 4>(a, batch);
   if (rc) return rc;
   if (splits > 1) {
-    rc = splitk_finalize(final_c, partial, (int)splits, a.M, a.N, a.bias, a.act, a.accumulate);
+    rc = splitk_finalize(final_c, partial, (int)splits, a.M, a.N, a.bias, a.act, a.accumulate, a.epi_tanh);
     pool_free(partial);
     if (rc) return rc;
   }

@@ -258,6 +258,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
 struct Params {
   float* C;
   const float* bias;
+  const float* epi_tanh;   // [M,N]: C = result * (1 - epi_tanh^2), or NULL
   long long M, N, K;
   int act, accumulate;
   int m_blocks, n_blocks, k_blocks;
@@ -609,6 +610,13 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
             }
             if (p.act == MT_ACT_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+            if (p.epi_tanh) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.epi_tanh + row * p.N + n));
+              v.x = __fmul_rn(v.x, __fsub_rn(1.f, __fmul_rn(t.x, t.x)));
+              v.y = __fmul_rn(v.y, __fsub_rn(1.f, __fmul_rn(t.y, t.y)));
+              v.z = __fmul_rn(v.z, __fsub_rn(1.f, __fmul_rn(t.z, t.z)));
+              v.w = __fmul_rn(v.w, __fsub_rn(1.f, __fmul_rn(t.w, t.w)));
+            }
             float4* dst = reinterpret_cast<float4*>(crow + n);
             if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
             *dst = v;
@@ -717,6 +725,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   Params p;
   p.C = a.C;
   p.bias = a.bias;
+  p.epi_tanh = a.epi_tanh;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.act = a.act;
   p.accumulate = a.accumulate;
@@ -763,6 +772,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
     if (rc) return rc;
     p.C = partial;
     p.bias = nullptr;
+    p.epi_tanh = nullptr;
     p.act = MT_ACT_NONE;
     p.accumulate = 0;
   }
@@ -803,7 +813,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   if (le != cudaSuccess) return fail(MT_ERR_CUDA, "gemm3xtf32 launch failed: %s", cudaGetErrorString(le));
   MT_LAUNCHED();
   if (partial) {
-    rc = splitk_finalize(a.C, partial, p.splits, a.M, a.N, a.bias, a.act, a.accumulate);
+    rc = splitk_finalize(a.C, partial, p.splits, a.M, a.N, a.bias, a.act, a.accumulate, a.epi_tanh);
     pool_free(partial);
     if (rc) return rc;
   }
@@ -839,7 +849,8 @@ int gemm_tc_try(const GemmArgs& a) {
   else return MT_ERR_UNSUPPORTED;
   // TMA: 16 B aligned bases and row pitches; epilogue: float4 rows of C / bias
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (!al16(a.A) || !al16(a.B) || !al16(a.C) || (a.bias && !al16(a.bias)) || (a.tanh_src && !al16(a.tanh_src)))
+  if (!al16(a.A) || !al16(a.B) || !al16(a.C) || (a.bias && !al16(a.bias)) || (a.tanh_src && !al16(a.tanh_src)) ||
+      (a.epi_tanh && !al16(a.epi_tanh)))
     return MT_ERR_UNSUPPORTED;
   if (lda % 4 || ldb % 4 || a.N % 4) return MT_ERR_UNSUPPORTED;
   // worthwhile shapes only: small / skinny problems are SIMT territory (HBM- or latency-bound)

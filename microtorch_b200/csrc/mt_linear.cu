@@ -50,8 +50,19 @@ MT_API int mt_linear_fwd_f32(float* Y, const float* X, const float* W, const flo
   return rc;
 }
 
+// Above this many dY elements the tanh' prologue is NOT fused into the two GEMMs: the Y tile costs a third of every
+// raw stage (3 instead of 5 TMA stages in flight) and measured 10.2 vs 7.9 ms per 65536x4096x4096 GEMM, while one
+// explicit dZ pass is 0.55 ms (profiles/r01_gemm_final_matrix.jsonl).  Small problems keep the fused form (one launch less).
+static long long g_prologue_fuse_max = 1ll << 22;
+extern "C" __attribute__((visibility("default"))) int mt_linear_set_prologue_fuse_max(long long elems) {
+  g_prologue_fuse_max = elems;
+  return MT_OK;
+}
+
 MT_API int mt_linear_bwd_f32(float* dX, float* dW, const float* dY, const float* Yact, const float* X, const float* W,
-                             int64_t M, int64_t N, int64_t K, int accumulate_dW) {
+                             int64_t M, int64_t N, int64_t K, int flags) {
+  const int accumulate_dW = flags & MT_LINEAR_ACCUMULATE_DW;
+  const bool dx_preact = (flags & MT_LINEAR_DX_TIMES_TANH_GRAD_OF_X) != 0;
   MT_REQUIRE_INIT();
   MT_CHECK_ARG(dW && dY && X && W, "mt_linear_bwd_f32: null pointer");
   MT_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "mt_linear_bwd_f32: negative extent");
@@ -68,6 +79,10 @@ MT_API int mt_linear_bwd_f32(float* dX, float* dW, const float* dY, const float*
     dZ = dZ_tmp;
     return rc;
   };
+  if (Yact && (long long)M * N > g_prologue_fuse_max) {   // large: one explicit dZ pass, then plain GEMMs
+    int rc0 = need_explicit();
+    if (rc0) return rc0;
+  }
   auto attempt = [&](GemmArgs a) -> int {
     // first with the fused prologue on tcgen05, then (if refused) SIMT on an explicit dZ
     if (g().gemm_engine_force != 0) {
@@ -106,6 +121,7 @@ MT_API int mt_linear_bwd_f32(float* dX, float* dW, const float* dY, const float*
     a.C = dX; a.B = W; a.M = M; a.N = K; a.K = N;
     a.a_sm = N; a.a_sk = 1;     // A(m, k'=n) = dY[m, n]
     a.b_sk = K; a.b_sn = 1;     // B(k'=n, n'=k) = W[n, k]
+    if (dx_preact) a.epi_tanh = X;   // X is the tanh output of the producing layer: emit ITS dZ directly
     rc = attempt(a);
   }
   if (dZ_tmp) pool_free(dZ_tmp);

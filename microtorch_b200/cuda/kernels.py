@@ -240,9 +240,16 @@ def linear_forward(x2d: DeviceArray, weight: DeviceArray, bias: Optional[DeviceA
     return out
 
 
+LINEAR_ACCUMULATE_DW = 1
+LINEAR_DX_TIMES_TANH_GRAD_OF_X = 2
+
+
 def linear_backward(grad_out: DeviceArray, y_act: Optional[DeviceArray], x2d: DeviceArray, weight: DeviceArray,
-                    need_dx: bool) -> Tuple[DeviceArray, Optional[DeviceArray]]:
-    """(dW, dX) of the fused Linear(+Tanh) node; tanh' applied in the GEMM prologue."""
+                    need_dx: bool, dx_preact: bool = False) -> Tuple[DeviceArray, Optional[DeviceArray]]:
+    """(dW, dX) of the fused Linear(+Tanh) node.  `y_act` given: grad_out is dL/dY and tanh' is applied first
+    (GEMM prologue or one explicit pass, the library decides); None: grad_out already is dL/dZ.
+    `dx_preact`: x2d is itself a tanh output, so dX is returned multiplied by (1 - x^2) in the GEMM epilogue -
+    i.e. as the pre-activation gradient of the layer that produced x."""
     g = grad_out.dense()
     x2d, weight = x2d.dense(), weight.dense()
     M, K = x2d.shape
@@ -251,7 +258,8 @@ def linear_backward(grad_out: DeviceArray, y_act: Optional[DeviceArray], x2d: De
     dX = DeviceArray.empty((M, K)) if need_dx else None
     ya = y_act.dense() if y_act is not None else None
     _capi.check(_lib().mt_linear_bwd_f32(dX.ptr if dX is not None else None, dW.ptr, g.ptr,
-                                         ya.ptr if ya is not None else None, x2d.ptr, weight.ptr, M, N, K, 0),
+                                         ya.ptr if ya is not None else None, x2d.ptr, weight.ptr, M, N, K,
+                                         LINEAR_DX_TIMES_TANH_GRAD_OF_X if (dx_preact and need_dx) else 0),
                 "mt_linear_bwd_f32")
     return dW, dX
 

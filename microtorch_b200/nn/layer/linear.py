@@ -54,8 +54,13 @@ class Linear(Module):
             out += b
         return out
 
-    def forward_fused(self, x: Tensor, activation: Optional[str] = None) -> Tensor:
-        """CUDA: act(X W^T + b) as one kernel and ONE tape node (activation None | "tanh")."""
+    def forward_fused(self, x: Tensor, activation: Optional[str] = None, x_fused_ctx: Optional[dict] = None) -> Tensor:
+        """CUDA: act(X W^T + b) as one kernel and ONE tape node (activation None | "tanh").
+
+        `x_fused_ctx`: set by Sequential when `x` is the PRIVATE output of the preceding fused
+        Linear+Tanh node (nobody else can hold it).  This node's dX epilogue then multiplies by
+        (1 - x^2) and hands the producer its pre-activation gradient dZ directly, so the producer
+        runs two plain GEMMs - tanh' fused into the producer side, no prologue, no extra pass."""
         self._check(x)
         K = backend_for(Device.CUDA).K
         weight, bias = self.weight, self.bias
@@ -66,16 +71,23 @@ class Linear(Module):
         y = y2d.reshape(lead + (self.out_features,))
         need_dx = x.requires_grad
         cache = {}
+        ctx = {"grad_is_preact": False}          # flipped by the next fused layer (see x_fused_ctx above)
+        chain = x_fused_ctx is not None and need_dx
+        if chain:
+            x_fused_ctx["grad_is_preact"] = True
 
         def both(g):
             """dW and dX come out of one C call; the two tape edges share the result."""
             if cache.get("for") is not g:
-                dW, dX = K.linear_backward(g.reshape((-1, self.out_features)), y2d if act else None, x2d,
-                                           weight.data, need_dx)
+                y_for_tanh = y2d if (act and not ctx["grad_is_preact"]) else None
+                dW, dX = K.linear_backward(g.reshape((-1, self.out_features)), y_for_tanh, x2d, weight.data,
+                                           need_dx, dx_preact=chain)
                 cache.update({"for": g, "dW": dW, "dX": dX.reshape(x.shape) if dX is not None else None})
             return cache
 
         deps = [Leaf(value=weight, grad_fn=lambda g: both(g)["dW"])]
         if need_dx:
             deps.append(Leaf(value=x, grad_fn=lambda g: both(g)["dX"]))
-        return Tensor(y, requires_grad=True, dependencies=deps, device=Device.CUDA, dtype=x.dtype)
+        out = Tensor(y, requires_grad=True, dependencies=deps, device=Device.CUDA, dtype=x.dtype)
+        out._fused_ctx = ctx if act else None
+        return out

@@ -38,6 +38,7 @@ class Sequential(Module):
     def forward(self, x: Tensor) -> Tensor:
         mods = self.modules
         i, n = 0, len(mods)
+        private_ctx = None      # tape context of x when x is an intermediate only this loop holds
         while i < n:
             m = mods[i]
             fuse = (type(m) is Linear and i + 1 < n and type(mods[i + 1]) is Tanh
@@ -47,9 +48,11 @@ class Sequential(Module):
                     if not getattr(part, "_device_initialized", False):
                         part.to(x.device)
                         part._device_initialized = True
-                x = m.forward_fused(x, activation="tanh")
+                x = m.forward_fused(x, activation="tanh", x_fused_ctx=private_ctx)
+                private_ctx = getattr(x, "_fused_ctx", None)
                 i += 2
             else:
                 x = m(x)
+                private_ctx = None
                 i += 1
         return x

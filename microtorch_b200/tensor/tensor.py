@@ -104,6 +104,7 @@ class Tensor(TensorLike):
         self._requires_grad = requires_grad
         self._grad = None
         self._grad_hook: Optional[Callable[["Tensor"], None]] = None
+        self._fused_ctx = None
         if requires_grad:
             self.zero_grad()
 

@@ -28,6 +28,7 @@ SOURCES = [
     "mt_reduce.cu",
     "mt_loss_sgd.cu",
     "mt_gemm_simt.cu",
+    "mt_gemm_skinny.cu",
     "mt_gemm_tc.cu",
     "mt_linear.cu",
     "mt_comm.cu",

@@ -30,6 +30,8 @@ int gemm_simt(GemmArgs a, long long batch);
 // C = act(sum_s partial[s] + bias) (+ C): deterministic fold of split-K partials stacked as [splits, M, N]
 int splitk_finalize(float* C, const float* partial, int splits, long long M, long long N, const float* bias, int act,
                     int accumulate, const float* epi_tanh);
+// HBM-bound kernels for tiny output widths (N <= 16); MT_ERR_UNSUPPORTED when the shape is not one of theirs
+int gemm_skinny_try(const GemmArgs& a);
 // MT_OK if the tcgen05 engine ran it, MT_ERR_UNSUPPORTED if the layout/shape is not one it
 // takes (caller falls back to SIMT), anything else is a real error.
 int gemm_tc_try(const GemmArgs& a);

@@ -150,6 +150,8 @@ int launch(const GemmArgs& a, long long batch) {
 
 namespace mt {
 
+static int g_skinny = 1;   // test hook: 0 routes tiny-N shapes through the generic tile as well
+
 int splitk_finalize(float* C, const float* partial, int splits, long long M, long long N, const float* bias, int act,
                     int accumulate, const float* epi_tanh) {
   float* sum = nullptr;
@@ -166,6 +168,10 @@ int splitk_finalize(float* C, const float* partial, int splits, long long M, lon
 int gemm_simt(GemmArgs a, long long batch) {
   if (a.M == 0 || a.N == 0 || batch == 0) return MT_OK;
   MT_CHECK_ARG(batch <= 65535, "matmul: batch %lld exceeds 65535", batch);
+  if (batch == 1 && g_skinny) {
+    int rc = gemm_skinny_try(a);
+    if (rc != MT_ERR_UNSUPPORTED) return rc;
+  }
   // tile choice
   int shape = 0;  // 0: 128x128, 1: 256x16 (skinny N), 2: 16x256 (skinny M)
   if (a.N <= 16 && a.M >= 64) shape = 1;
@@ -224,6 +230,11 @@ MT_API int mt_matmul_f32(float* C, const float* A, const float* B, int64_t batch
   }
   g().gemm_last_engine = 0;
   return gemm_simt(a, batch);
+}
+
+extern "C" __attribute__((visibility("default"))) int mt_gemm_set_skinny(int v) {
+  mt::g_skinny = v ? 1 : 0;
+  return MT_OK;
 }
 
 MT_API int mt_gemm_last_engine(int* engine) {

@@ -1,0 +1,299 @@
+// mt_gemm_skinny.cu - HBM-bound kernels for Linear layers with a tiny output width (N <= 16).
+//
+// The 4096->10 head of BASELINE.json config #2 is three "GEMMs" of 5.4 GFLOP each that read or write
+// 1 GiB: they are bandwidth problems, not tensor-core problems.  The generic
+// 128x128 SIMT tile wastes 92 % of its work on them (0.48 / 1.47 / 1.05 ms measured); these kernels stream
+// the big operand once with 128-bit coalesced accesses and keep the small one on chip.
+//
+//   skinny_fwd : Y[M,N]  = act(X[M,K] . W[N,K]^T + b)        W (N*K*4 B <= 200 KB) in shared memory
+//   skinny_dx  : dX[M,K] = dZ[M,N] . W[N,K]  (* (1 - X^2))   W in shared memory, dZ rows in registers
+//   skinny_dw  : dW[N,K] (+)= dZ[M,N]^T . X[M,K]             per-CTA row slabs, partials folded deterministically
+//
+// Algorithmic traffic: fwd 4*M*K + 4*M*N; dx 4*M*K (+4*M*K with the tanh' epilogue) + 4*M*N; dw 4*M*K + 4*M*N.
+// Reference call sites: the same matmul / bkwd_a / bkwd_b of src/tensor/ops/overload.py:132-154 as the big GEMMs.
+#include <algorithm>
+
+#include "mt_common.cuh"
+#include "mt_gemm.cuh"
+
+using namespace mt;
+
+namespace {
+
+constexpr int THREADS = 512;
+constexpr int RB = 4;                       // rows per warp iteration (register blocking over the smem-resident W)
+constexpr int SMEM_W_MAX = 200 * 1024;
+
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int NP>
+__global__ void __launch_bounds__(THREADS) skinny_fwd_kernel(float* __restrict__ Y, const float* __restrict__ X,
+                                                             const float* __restrict__ W, const float* __restrict__ bias,
+                                                             long long M, int N, long long K, long long ldx, long long ldw,
+                                                             int act) {
+  extern __shared__ float4 Ws[];            // [N][K/4]
+  const int K4 = (int)(K >> 2);
+  for (int i = threadIdx.x; i < N * K4; i += THREADS) {
+    const int n = i / K4, c = i - n * K4;
+    Ws[i] = __ldg(reinterpret_cast<const float4*>(W + n * ldw) + c);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warps = (long long)gridDim.x * (THREADS / 32);
+  for (long long r0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * RB; r0 < M; r0 += warps * RB) {
+    float acc[RB][NP];
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int n = 0; n < NP; ++n) acc[i][n] = 0.f;
+    for (int c = lane; c < K4; c += 32) {
+      float4 x[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i)
+        x[i] = (r0 + i < M) ? mtd::ld_stream4(X + (r0 + i) * ldx + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        if (n < N) {
+          const float4 w = Ws[n * K4 + c];
+#pragma unroll
+          for (int i = 0; i < RB; ++i) acc[i][n] += dot4(x[i], w);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+#pragma unroll
+      for (int n = 0; n < NP; ++n) acc[i][n] = mtd::warp_sum(acc[i][n]);
+    // lanes 0..N-1 each finish one output column of the RB rows
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      if (r0 + i < M) {
+        float v = 0.f;
+#pragma unroll
+        for (int n = 0; n < NP; ++n)
+          if (lane == n) v = acc[i][n];
+        if (lane < N) {
+          if (bias) v += __ldg(bias + lane);
+          if (act == MT_ACT_TANH) v = tanhf(v);
+          Y[(r0 + i) * N + lane] = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dX
+template <int NP>
+__global__ void __launch_bounds__(THREADS) skinny_dx_kernel(float* __restrict__ dX, const float* __restrict__ dZ,
+                                                            const float* __restrict__ W, const float* __restrict__ epi_tanh,
+                                                            long long M, int N, long long K, long long ldz, long long ldw) {
+  extern __shared__ float4 Ws[];            // [N][K/4]
+  const int K4 = (int)(K >> 2);
+  for (int i = threadIdx.x; i < N * K4; i += THREADS) {
+    const int n = i / K4, c = i - n * K4;
+    Ws[i] = __ldg(reinterpret_cast<const float4*>(W + n * ldw) + c);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warps = (long long)gridDim.x * (THREADS / 32);
+  for (long long r0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * RB; r0 < M; r0 += warps * RB) {
+    float dz[RB][NP];
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const float mine = (lane < N && r0 + i < M) ? __ldg(dZ + (r0 + i) * ldz + lane) : 0.f;
+#pragma unroll
+      for (int n = 0; n < NP; ++n) dz[i][n] = __shfl_sync(0xffffffffu, mine, n);
+    }
+    for (int c = lane; c < K4; c += 32) {
+      float4 o[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        if (n < N) {
+          const float4 w = Ws[n * K4 + c];
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            o[i].x = fmaf(dz[i][n], w.x, o[i].x);
+            o[i].y = fmaf(dz[i][n], w.y, o[i].y);
+            o[i].z = fmaf(dz[i][n], w.z, o[i].z);
+            o[i].w = fmaf(dz[i][n], w.w, o[i].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        if (r0 + i < M) {
+          float4 v = o[i];
+          if (epi_tanh) {
+            const float4 t = mtd::ld_stream4(epi_tanh + (r0 + i) * K + 4 * c);
+            v.x = __fmul_rn(v.x, __fsub_rn(1.f, __fmul_rn(t.x, t.x)));
+            v.y = __fmul_rn(v.y, __fsub_rn(1.f, __fmul_rn(t.y, t.y)));
+            v.z = __fmul_rn(v.z, __fsub_rn(1.f, __fmul_rn(t.z, t.z)));
+            v.w = __fmul_rn(v.w, __fsub_rn(1.f, __fmul_rn(t.w, t.w)));
+          }
+          mtd::st4(dX + (r0 + i) * K + 4 * c, v);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dW
+// CTA b sums rows [b*slab, (b+1)*slab) of dZ^T.X into partial[b][N][K]; thread t owns float4 columns t, t+512, ...
+constexpr int DZ_ROWS = 64;                 // dZ rows staged in shared memory per step
+
+template <int NP, int CG>
+__global__ void __launch_bounds__(THREADS) skinny_dw_kernel(float* __restrict__ partial, const float* __restrict__ dZ,
+                                                            const float* __restrict__ X, long long M, int N, long long K,
+                                                            long long ldz, long long ldx, long long slab) {
+  __shared__ float dzs[DZ_ROWS][NP];
+  const int K4 = (int)(K >> 2);
+  const long long m_begin = (long long)blockIdx.x * slab;
+  const long long m_end = m_begin + slab < M ? m_begin + slab : M;
+  float4 acc[CG][NP];
+#pragma unroll
+  for (int g = 0; g < CG; ++g)
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[g][n] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long mb = m_begin; mb < m_end; mb += DZ_ROWS) {
+    const int rows = (int)(m_end - mb < DZ_ROWS ? m_end - mb : DZ_ROWS);
+    __syncthreads();
+    for (int i = threadIdx.x; i < DZ_ROWS * NP; i += THREADS) {
+      const int r = i / NP, n = i - r * NP;
+      dzs[r][n] = (r < rows && n < N) ? __ldg(dZ + (mb + r) * ldz + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int r = 0; r < rows; ++r) {
+      float4 x[CG];
+#pragma unroll
+      for (int g = 0; g < CG; ++g) {
+        const int c = threadIdx.x + g * THREADS;
+        x[g] = (c < K4) ? mtd::ld_stream4(X + (mb + r) * ldx + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const float d = dzs[r][n];          // broadcast read
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+          acc[g][n].x = fmaf(d, x[g].x, acc[g][n].x);
+          acc[g][n].y = fmaf(d, x[g].y, acc[g][n].y);
+          acc[g][n].z = fmaf(d, x[g].z, acc[g][n].z);
+          acc[g][n].w = fmaf(d, x[g].w, acc[g][n].w);
+        }
+      }
+    }
+  }
+  float* out = partial + (long long)blockIdx.x * N * K;
+#pragma unroll
+  for (int g = 0; g < CG; ++g) {
+    const int c = threadIdx.x + g * THREADS;
+    if (c < K4) {
+#pragma unroll
+      for (int n = 0; n < NP; ++n)
+        if (n < N) mtd::st4(out + (long long)n * K + 4 * c, acc[g][n]);
+    }
+  }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int NP>
+int run_fwd(const GemmArgs& a, long long ldx, long long ldw) {
+  const size_t smem = (size_t)a.N * a.K * 4;
+  auto kern = skinny_fwd_kernel<NP>;
+  static bool set = false;
+  if (!set) { MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_MAX)); set = true; }
+  const int grid = (int)std::min<long long>(g().sm_count, ceil_div(a.M, (THREADS / 32) * RB));
+  kern<<<grid, THREADS, smem, g().stream>>>(a.C, a.A, a.B, a.bias, a.M, (int)a.N, a.K, ldx, ldw, a.act);
+  MT_LAUNCHED();
+  return MT_OK;
+}
+
+template <int NP>
+int run_dx(const GemmArgs& a, long long ldz, long long ldw) {
+  // GEMM view: M x N_out(=a.N, the wide K of the layer) with reduction a.K (= the layer's tiny N)
+  const size_t smem = (size_t)a.K * a.N * 4;
+  auto kern = skinny_dx_kernel<NP>;
+  static bool set = false;
+  if (!set) { MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_MAX)); set = true; }
+  const int grid = (int)std::min<long long>(g().sm_count, ceil_div(a.M, (THREADS / 32) * RB));
+  kern<<<grid, THREADS, smem, g().stream>>>(a.C, a.A, a.B, a.epi_tanh, a.M, (int)a.K, a.N, ldz, ldw);
+  MT_LAUNCHED();
+  return MT_OK;
+}
+
+template <int NP>
+int run_dw(const GemmArgs& a, long long ldz, long long ldx) {
+  // GEMM view: rows M (= tiny layer N), columns a.N (= layer K), reduction a.K (= batch rows)
+  const long long rows = a.K, Kc = a.N;
+  const int K4 = (int)(Kc / 4);
+  const int cg = (int)ceil_div(K4, THREADS);
+  long long ctas = std::min<long long>((long long)g().sm_count, ceil_div(rows, 256));
+  const long long slab = ceil_div(ceil_div(rows, ctas), DZ_ROWS) * DZ_ROWS;
+  ctas = ceil_div(rows, slab);
+  float* partial = nullptr;
+  int rc = pool_alloc((void**)&partial, sizeof(float) * (size_t)ctas * a.M * Kc);
+  if (rc) return rc;
+#define MT_DW(CGV) skinny_dw_kernel<NP, CGV><<<(int)ctas, THREADS, 0, g().stream>>>(partial, a.A, a.B, rows, (int)a.M, Kc, ldz, ldx, slab)
+  switch (cg) {
+    case 1: MT_DW(1); break;
+    case 2: MT_DW(2); break;
+    case 3: MT_DW(3); break;
+    default: MT_DW(4); break;
+  }
+#undef MT_DW
+  MT_LAUNCHED();
+  rc = splitk_finalize(a.C, partial, (int)ctas, a.M, Kc, nullptr, MT_ACT_NONE, a.accumulate, nullptr);
+  pool_free(partial);
+  return rc;
+}
+
+template <typename F4, typename F8, typename F12, typename F16>
+int by_np(long long n, F4 f4, F8 f8, F12 f12, F16 f16) {
+  if (n <= 4) return f4();
+  if (n <= 8) return f8();
+  if (n <= 12) return f12();
+  return f16();
+}
+
+}  // namespace
+
+namespace mt {
+
+int gemm_skinny_try(const GemmArgs& a) {
+  if (a.tanh_src) return MT_ERR_UNSUPPORTED;
+  // ---- forward shape: tiny N, A row-major [M,K], B(k,n) = W[n*ldw + k]
+  if (a.N <= 16 && a.N >= 1 && a.M >= 256 && a.K >= 128 && a.a_sk == 1 && a.b_sk == 1 && !a.accumulate && !a.epi_tanh) {
+    const long long ldx = a.a_sm, ldw = a.b_sn;
+    if (a.K % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0 && al16(a.A) && al16(a.B) && a.N * a.K * 4 <= SMEM_W_MAX)
+      return by_np(a.N, [&] { return run_fwd<4>(a, ldx, ldw); }, [&] { return run_fwd<8>(a, ldx, ldw); },
+                   [&] { return run_fwd<12>(a, ldx, ldw); }, [&] { return run_fwd<16>(a, ldx, ldw); });
+  }
+  // ---- dX shape: tiny reduction, A row-major [M,Kr], B(k,n) = W[k*ldw + n], wide output
+  if (a.K <= 16 && a.K >= 1 && a.M >= 256 && a.N >= 128 && a.a_sk == 1 && a.b_sn == 1 && !a.accumulate && !a.bias &&
+      a.act == MT_ACT_NONE) {
+    const long long ldz = a.a_sm, ldw = a.b_sk;
+    if (a.N % 4 == 0 && ldw % 4 == 0 && al16(a.B) && al16(a.C) && (!a.epi_tanh || al16(a.epi_tanh)) &&
+        a.K * a.N * 4 <= SMEM_W_MAX)
+      return by_np(a.K, [&] { return run_dx<4>(a, ldz, ldw); }, [&] { return run_dx<8>(a, ldz, ldw); },
+                   [&] { return run_dx<12>(a, ldz, ldw); }, [&] { return run_dx<16>(a, ldz, ldw); });
+  }
+  // ---- dW shape: tiny M, A(m,k) = dZ[k*ldz + m], B(k,n) = X[k*ldx + n], long reduction
+  if (a.M <= 16 && a.M >= 1 && a.N >= 128 && a.K >= 1024 && a.a_sm == 1 && a.b_sn == 1 && !a.bias && a.act == MT_ACT_NONE &&
+      !a.epi_tanh) {
+    const long long ldz = a.a_sk, ldx = a.b_sk;
+    // accumulators per thread = CG x NP float4: beyond 24 the kernel spills (ptxas -v), leave those to the generic tile
+    const long long cg_need = ceil_div(a.N / 4, THREADS), np_need = ceil_div(a.M, 4) * 4;
+    if (a.N % 4 == 0 && ldx % 4 == 0 && al16(a.B) && al16(a.C) && cg_need <= 4 && cg_need * np_need <= 24)
+      return by_np(a.M, [&] { return run_dw<4>(a, ldz, ldx); }, [&] { return run_dw<8>(a, ldz, ldx); },
+                   [&] { return run_dw<12>(a, ldz, ldx); }, [&] { return run_dw<16>(a, ldz, ldx); });
+  }
+  return MT_ERR_UNSUPPORTED;
+}
+
+}  // namespace mt

@@ -49,17 +49,23 @@ __global__ void __launch_bounds__(THREADS) skinny_fwd_kernel(float* __restrict__
     for (int i = 0; i < RB; ++i)
 #pragma unroll
       for (int n = 0; n < NP; ++n) acc[i][n] = 0.f;
-    for (int c = lane; c < K4; c += 32) {
-      float4 x[RB];
+    // two column chunks per iteration: 2*RB independent 128-bit loads in flight per lane
+    for (int c = lane; c < K4; c += 64) {
+      float4 x[2][RB];
+      const bool second = (c + 32 < K4);
 #pragma unroll
-      for (int i = 0; i < RB; ++i)
-        x[i] = (r0 + i < M) ? mtd::ld_stream4(X + (r0 + i) * ldx + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < RB; ++i)
+          x[h][i] = (r0 + i < M && (h == 0 || second)) ? mtd::ld_stream4(X + (r0 + i) * ldx + 4 * (c + 32 * h))
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int n = 0; n < NP; ++n) {
         if (n < N) {
-          const float4 w = Ws[n * K4 + c];
+          const float4 w0 = Ws[n * K4 + c];
+          const float4 w1 = second ? Ws[n * K4 + c + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < RB; ++i) acc[i][n] += dot4(x[i], w);
+          for (int i = 0; i < RB; ++i) acc[i][n] += dot4(x[0][i], w0) + dot4(x[1][i], w1);
         }
       }
     }

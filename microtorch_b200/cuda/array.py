@@ -180,6 +180,10 @@ class DeviceArray:
             return out
         if self.is_dense:
             _capi.check(_capi.lib().mt_d2d(out.ptr, self.ptr, out.nbytes), "mt_d2d")
+        elif self.dtype == F32 and any(s == 0 and d > 1 for d, s in zip(self.shape, self.strides)):
+            # broadcast view: x * 1 through the broadcasting kernel (vectorised row/column/scalar paths, exact)
+            from . import kernels as K
+            K.binary(_capi.BIN_MUL, self, _one(), out=out)
         else:
             self._require_f32("copy of a strided view")
             _capi.check(_capi.lib().mt_copy_strided_f32(out.ptr, self.ptr, self.ndim, _capi.i64(self.shape),
@@ -392,6 +396,16 @@ class DeviceArray:
                                   "returns CPU tensors here and cannot work either, SURVEY.md Q8)")
     __lt__ = __gt__ = __le__ = __ge__ = _unsupported_compare
     __hash__ = object.__hash__
+
+
+_ONE = None
+
+
+def _one() -> DeviceArray:
+    global _ONE
+    if _ONE is None:
+        _ONE = DeviceArray.from_host(1.0)
+    return _ONE
 
 
 def _as_device(x) -> DeviceArray:

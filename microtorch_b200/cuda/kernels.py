@@ -51,8 +51,17 @@ def inplace(op: int, dst: DeviceArray, src) -> DeviceArray:
     return dst
 
 
+def _unbroadcast_view(x: DeviceArray) -> DeviceArray:
+    """The distinct elements of a broadcast (stride-0) view: extent 1 wherever the stride is 0."""
+    idx = tuple(slice(0, 1) if (s == 0 and d > 1) else slice(None) for d, s in zip(x.shape, x.strides))
+    return x[idx]
+
+
 def unary(op: int, x: DeviceArray, scalar: float = 0.0) -> DeviceArray:
     x = _as_device(x)
+    if x.size and any(s == 0 and d > 1 for d, s in zip(x.shape, x.strides)):
+        # f(broadcast(v)) == broadcast(f(v)): touch only the distinct elements (e.g. -g for g = sum().backward())
+        return unary(op, _unbroadcast_view(x), scalar).broadcast_to(x.shape)
     src = x.dense()
     out = DeviceArray.empty(x.shape)
     if out.size:
@@ -128,12 +137,18 @@ def reduce_sum(x: DeviceArray, reduce_axes: Sequence[int], other: Optional[Devic
     pass when its layout allows, otherwise multiplied first."""
     x = _as_device(x)
     shape = x.shape
+    red_set = {int(a) % max(len(shape), 1) for a in reduce_axes}
+    kept = [d for i, d in enumerate(shape) if i not in red_set]
+    if other is None and x.size and all(x.strides[a] == 0 or shape[a] == 1 for a in red_set) \
+            and any(shape[a] > 1 for a in red_set):
+        # the view is constant along every reduced axis (a broadcast gradient): sum == value * count
+        count = _numel([shape[a] for a in red_set])
+        idx = tuple(slice(0, 1) if i in red_set else slice(None) for i in range(len(shape)))
+        return unary(_capi.UN_SCALE, x[idx], float(count)).dense().reshape(kept)
     if other is not None:
         other = _as_device(other).broadcast_to(shape)
     src = x.dense()
     passes = plan_reduction(shape, reduce_axes)
-    red_set = {int(a) % max(len(shape), 1) for a in reduce_axes}
-    kept = [d for i, d in enumerate(shape) if i not in red_set]
     if not passes:                          # nothing to add up (all reduced extents are 1)
         res = src if other is None else binary(_capi.BIN_MUL, src, other)
         return res.reshape(kept)

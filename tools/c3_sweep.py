@@ -96,10 +96,21 @@ def main():
         work["sum_axis0"] = (lambda: x.sum(axis=0), B)
         work["sum_axis1"] = (lambda: x.sum(axis=1), B)
         xd = x.data
+        yd = Tensor(ys["same"], device="cuda").data
         from microtorch_b200.cuda import kernels as K
-        work["k_add_same"] = (lambda: K.binary(_capi.BIN_ADD, xd, xd), 3 * B)
+        work["k_add_same"] = (lambda: K.binary(_capi.BIN_ADD, xd, yd), 3 * B)          # raw kernels, distinct operands
         work["k_tanh"] = (lambda: K.unary(_capi.UN_TANH, xd), 2 * B)
-        work["k_tanh_bwd"] = (lambda: K.binary(_capi.BIN_TANH_BWD, xd, xd), 3 * B)
+        work["k_tanh_bwd"] = (lambda: K.binary(_capi.BIN_TANH_BWD, xd, yd), 3 * B)
+        work["k_mul_reduce_cols"] = (lambda: K.reduce_sum(xd, (0,), yd), 2 * B)         # fused grad*other + unbroadcast
+        from microtorch_b200.nn.loss import MSELoss
+        lossf = MSELoss()
+        xp = Tensor(xd, requires_grad=True, device="cuda")
+        yt = Tensor(yd, device="cuda")
+
+        def f_loss():
+            xp.zero_grad()
+            lossf(xp, yt).backward()
+        work["mse_loss_fwd_bwd"] = (f_loss, 3 * B)
         for name, (fn, nbytes) in work.items():
             if args.only and args.only not in name:
                 continue

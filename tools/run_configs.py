@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""Measure the BASELINE.json configs other than the bench headline through the public API (run under gpurun):
+
+  c1a / c1b   spiral demo on device="cuda": steps/s (latency-bound), loss parity with the notebook stream
+  c4          3-D Linear stack (256 x 512 x 2048, k layers) + BCELoss: samples/s, GEMM TFLOP/s
+  c5          4096-wide x 8 layers, 65536 rows per GPU (the per-GPU share of global batch 524288 at 8 GPUs)
+
+One JSON line per config; `--cpu` adds the oracle (CPU port of the reference) on a bounded sample."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--cpu", action="store_true")
+    ap.add_argument("--c4-layers", type=int, default=2)
+    args = ap.parse_args()
+    from microtorch_b200 import _capi, workloads as W
+    _capi.require_device(0)
+    lib = _capi.lib()
+    import microtorch_b200.nn as nn
+    from microtorch_b200.nn.activation import Tanh
+    from microtorch_b200.nn.loss import BCELoss, CrossEntropyLoss, MSELoss
+    from microtorch_b200.nn.optimizer import SGD
+    from microtorch_b200.tensor import Tensor
+    from microtorch_b200.trainer import train_step
+    losses = {"mse": MSELoss, "ce": CrossEntropyLoss, "bce": BCELoss}
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    lib.mt_event_create(C.byref(e0))
+    lib.mt_event_create(C.byref(e1))
+
+    def run(wl, steps, warmup, tag, extra=None):
+        model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+        X, T = Tensor(x, device="cuda"), Tensor(t, device="cuda")
+        loss_fn, opt = losses[wl.loss](), SGD(model.parameters, lr=wl.lr)
+        first = None
+        for _ in range(warmup):
+            l = train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim)
+            if first is None:
+                first = l.item()
+        lib.mt_sync()
+        lib.mt_prof_reset()
+        lib.mt_prof_enable(1)
+        lib.mt_launch_count_reset()
+        lib.mt_event_record(e0)
+        for _ in range(steps):
+            l = train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim)
+        lib.mt_event_record(e1)
+        lib.mt_event_sync(e1)
+        ms = C.c_float()
+        lib.mt_event_elapsed_ms(e0, e1, C.byref(ms))
+        n, gms, gfl, nl = C.c_uint64(), C.c_double(), C.c_double(), C.c_uint64()
+        lib.mt_prof_gemm(C.byref(n), C.byref(gms), C.byref(gfl))
+        lib.mt_prof_enable(0)
+        lib.mt_launch_count(C.byref(nl))
+        rows = int(np.prod(x.shape[:-1]))
+        rec = {"config": tag, "steps": steps, "ms_per_step": ms.value / steps, "steps_per_s": steps / (ms.value / 1e3),
+               "samples_per_s": wl.batch * steps / (ms.value / 1e3), "rows_per_step": rows, "first_loss": first,
+               "last_loss": l.item(), "launches_per_step": nl.value / steps,
+               "tcgen05_gemm_ms_per_step": gms.value / steps,
+               "tcgen05_gemm_tflops": (gfl.value / gms.value / 1e9) if gms.value else None}
+        if extra:
+            rec.update(extra)
+        print(json.dumps(rec), flush=True)
+        del model, X, T
+        lib.mt_pool_trim()
+
+    def cpu(wl, steps, tag):
+        from oracle import workloads as OW
+        from oracle.nnref import train_step as ostep
+        model, x, t = OW.setup(wl)
+        ostep(model, x, t, wl.loss, wl.lr, wl.pred_map, wl.squeeze_dim, x.ndim == 3)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ostep(model, x, t, wl.loss, wl.lr, wl.pred_map, wl.squeeze_dim, x.ndim == 3)
+        dt = (time.perf_counter() - t0) / steps
+        print(json.dumps({"config": tag + "_cpu_oracle", "ms_per_step": dt * 1e3, "samples_per_s": wl.batch / dt,
+                          "host_cpus": os.cpu_count()}), flush=True)
+
+    want = lambda k: (not args.only) or k in args.only.split(",")
+    if want("c1a"):
+        run(W.C1A, 2000, 50, "c1a_spiral_notebook_mlp_2_64_32_16_1")
+        if args.cpu:
+            cpu(W.C1A, 500, "c1a")
+    if want("c1b"):
+        run(W.C1B, 2000, 50, "c1b_spiral_2_100_3")
+        if args.cpu:
+            cpu(W.C1B, 500, "c1b")
+    if want("c4"):
+        k = args.c4_layers
+        wl = W.Workload("c4", (2048,) * (k + 1), "bce", 0.01, 256, pred_map=(0.49, 0.5), seed=0, input_shape=(256, 512, 2048))
+        run(wl, 5, 2, f"c4_3d_linear_256x512x2048_k{k}_bce", {"gemm_flops_per_step": wl.gemm_flops_per_step()})
+        if args.cpu:
+            cpu(W.Workload("c4s", (2048,) * (k + 1), "bce", 0.01, 8, pred_map=(0.49, 0.5), seed=0, input_shape=(8, 512, 2048)),
+                1, "c4_at_8x512x2048")
+    if want("c5"):
+        wl = W.scaled(W.C5, 65536)
+        run(wl, 4, 2, "c5_mlp_4096x8_rows65536_per_gpu", {"gemm_flops_per_step": wl.gemm_flops_per_step()})
+        if args.cpu:
+            cpu(W.scaled(W.C5, 2048), 1, "c5_at_2048_rows")
+
+
+if __name__ == "__main__":
+    main()

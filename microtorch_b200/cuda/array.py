@@ -64,7 +64,7 @@ def _numel(shape: Sequence[int]) -> int:
 
 
 class DeviceArray:
-    __slots__ = ("_block", "ptr", "shape", "strides", "dtype", "_host_value", "_owned", "__weakref__")
+    __slots__ = ("_block", "ptr", "shape", "strides", "dtype", "_host_value", "_owned", "_const", "__weakref__")
     __array_priority__ = 1000       # numpy scalars defer to our reflected operators
 
     def __init__(self, block: _Block, ptr: int, shape: Sequence[int], strides: Sequence[int],
@@ -75,7 +75,8 @@ class DeviceArray:
         self.strides = tuple(int(s) for s in strides)      # in ELEMENTS
         self.dtype = np.dtype(dtype)
         self._host_value = None     # host mirror of a 0-d constant built from a Python scalar
-        self._owned = False         # adopted as some tensor's .grad (see Tensor._accumulate)
+        self._owned = False         # adopted as some tensor's .grad (see Tensor._receive)
+        self._const = False         # shared read-only constant (device_constant): never adopted, never written
 
     # ------------------------------------------------------------------ constructors
     @classmethod
@@ -197,6 +198,8 @@ class DeviceArray:
 
     def fill(self, value: float) -> None:
         self._require_f32("fill")
+        if self._const:
+            raise ValueError("this array is a shared read-only constant")
         if not self.size:
             return
         if not self.is_dense:
@@ -396,6 +399,24 @@ class DeviceArray:
                                   "returns CPU tensors here and cannot work either, SURVEY.md Q8)")
     __lt__ = __gt__ = __le__ = __ge__ = _unsupported_compare
     __hash__ = object.__hash__
+
+
+_CONSTS: dict = {}
+
+
+def device_constant(value: float) -> "DeviceArray":
+    """A shared, read-only 0-d device array for a Python scalar operand (`x * 0.49`, `/ count`, the backward seed).
+    Uploading a scalar is a blocking 4-byte H2D copy; operands coerced inside ops are never written, so they
+    are uploaded once per distinct value."""
+    key = float(np.float32(value))
+    arr = _CONSTS.get(key)
+    if arr is None:
+        if len(_CONSTS) > 4096:
+            _CONSTS.clear()
+        arr = DeviceArray.from_host(key)
+        arr._const = True
+        _CONSTS[key] = arr
+    return arr
 
 
 _ONE = None

@@ -41,6 +41,8 @@ def binary(op: int, a, b, scalar: float = 0.0, out: Optional[DeviceArray] = None
 def inplace(op: int, dst: DeviceArray, src) -> DeviceArray:
     """dst (op)= src, broadcasting src; dst may be a strided view (np.add(a, b, out=a))."""
     src = _as_device(src)
+    if dst._const:
+        raise ValueError("in-place update of a shared read-only constant")
     if broadcast_shape(dst.shape, src.shape) != dst.shape:
         raise ValueError(f"non-broadcastable output operand with shape {dst.shape}")
     sv = src.broadcast_to(dst.shape)
@@ -147,6 +149,15 @@ def reduce_sum(x: DeviceArray, reduce_axes: Sequence[int], other: Optional[Devic
         return unary(_capi.UN_SCALE, x[idx], float(count)).dense().reshape(kept)
     if other is not None:
         other = _as_device(other).broadcast_to(shape)
+        bcast = lambda a: all(st == 0 or d == 1 for d, st in zip(a.shape, a.strides))
+        if x.size and bcast(other):         # sum(x * c) == c * sum(x): c is one broadcast scalar
+            c = other[(0,) * len(shape)]
+            return binary(_capi.BIN_MUL, reduce_sum(x, reduce_axes), c)
+        if x.size and bcast(x):             # sum(c * other) == c * sum(other)  (c = sum().backward()'s gradient)
+            c = x[(0,) * len(shape)]
+            return binary(_capi.BIN_MUL, reduce_sum(other, reduce_axes), c)
+        if not x.is_dense and other.is_dense:
+            x, other = other, x             # the kernel streams its first operand densely, the second may be strided
     src = x.dense()
     passes = plan_reduction(shape, reduce_axes)
     if not passes:                          # nothing to add up (all reduced extents are 1)

@@ -37,8 +37,14 @@ def is_tensorlike(obj: object) -> TypeGuard[TensorLike]:
 
 
 def data_cast(t: Union[Data, "Tensor"], device: Device) -> "Tensor":
-    """Anything that is not a Tensor becomes one on `device`."""
-    return t if isinstance(t, Tensor) else Tensor(t, device=device)
+    """Anything that is not a Tensor becomes one on `device`.  A Python scalar operand of a CUDA op becomes a
+    shared read-only device constant (uploaded once per value) instead of a blocking 4-byte copy per use."""
+    if isinstance(t, Tensor):
+        return t
+    if device == Device.CUDA and isinstance(t, (int, float)) and not isinstance(t, bool):
+        from ..cuda.array import device_constant
+        return Tensor(device_constant(t), device=device)
+    return Tensor(t, device=device)
 
 
 def data_gate(fn):
@@ -257,7 +263,7 @@ class Tensor(TensorLike):
         if cur is None or cur is _LAZY:
             # adopt; an array already adopted elsewhere is copied so two tensors never share a
             # buffer that zero_grad()/SGD may later write in place
-            if g._owned:
+            if g._owned or g._const:
                 g = g.copy()
             g._owned = True
             self._grad = g
@@ -271,7 +277,11 @@ class Tensor(TensorLike):
             raise ValueError("Backward was called on a non-required-grad tensor!")
         if grad is None:
             if self.shape == ():
-                grad = self.build_ndarray(1.0, self.dtype, self.device)
+                if self.device == Device.CUDA:
+                    from ..cuda.array import device_constant
+                    grad = device_constant(1.0)
+                else:
+                    grad = self.build_ndarray(1.0, self.dtype, self.device)
             else:
                 raise ValueError(f"Grad must be provided for non-scalar tensors. Tensor shape: {self.shape}")
         if isinstance(grad, np.generic) and self.device == Device.CPU:

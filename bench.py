@@ -294,20 +294,22 @@ def main():
     value = samples / (ms_total / 1e3)
 
     # ------------------------------------------------------------- end-to-end arm (host inputs every step)
-    hx, ht = C.c_void_p(), C.c_void_p()
-    _capi.check(lib.mt_host_alloc(C.byref(hx), x_host.nbytes))
-    _capi.check(lib.mt_host_alloc(C.byref(ht), t_host.nbytes))
-    px = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_float)), shape=x_host.shape)
-    pt = np.ctypeslib.as_array(C.cast(ht, C.POINTER(C.c_float)), shape=t_host.shape)
+    from microtorch_b200 import cuda as mtcuda
+    px, pt = mtcuda.pinned_empty(x_host.shape), mtcuda.pinned_empty(t_host.shape)     # pinned host staging
     px[...] = x_host
     pt[...] = t_host
     e2e_loss = []
+    pending = {"x": mtcuda.prefetch(px), "t": mtcuda.prefetch(pt)}     # upload of the first batch
 
     def step_e2e():
-        xs = Tensor(px, device="cuda")           # public API: H2D from pinned host memory
-        ts = Tensor(pt, device="cuda")
+        # public API, double-buffered: this step's inputs were uploaded from pinned host memory while the previous
+        # step computed; the next step's upload is issued now and overlaps this step.  The loss is read back (D2H)
+        # every step.  All of it is inside the timed region.
+        mtcuda.wait_prefetch()
+        xs, ts = Tensor(pending["x"], device="cuda"), Tensor(pending["t"], device="cuda")
+        pending["x"], pending["t"] = mtcuda.prefetch(px), mtcuda.prefetch(pt)
         loss = trainer.step(xs, ts)
-        e2e_loss.append(loss.item())             # D2H read of the step's result
+        e2e_loss.append(loss.item())
 
     step_e2e()
     e2e_steps = max(3, min(args.steps, 10))

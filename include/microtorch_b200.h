@@ -64,6 +64,14 @@ int mt_event_destroy(void* ev);
 /* number of kernels this library has launched since the last reset (bench "gpu_launches") */
 int mt_launch_count(uint64_t* count);
 int mt_launch_count_reset(void);
+/* Whole-step CUDA graphs (the user loop demo.ipynb:5178-5189 is launch-latency-bound at the
+ * spiral-demo sizes).  Every launch made between begin and end is captured instead of executed; blocking calls
+ * (mt_h2d, mt_d2h, mt_sync) are not allowed inside.  Pool blocks allocated during the capture stay reserved for the
+ * graph (its kernels write them on every replay) until mt_graph_destroy.                                        */
+int mt_graph_begin(void);
+int mt_graph_end(void** graph_handle);
+int mt_graph_launch(void* graph_handle);
+int mt_graph_destroy(void* graph_handle);
 /* overwrite a buffer larger than L2 (timing hygiene between timed iterations)           */
 int mt_l2_flush(void);
 /* per-kernel timing of the dominant kernel (bench roofline): when enabled, every tcgen05
@@ -90,6 +98,11 @@ int mt_h2d(void* dst, const void* src, size_t bytes);        /* blocks until src
 int mt_d2h(void* dst, const void* src, size_t bytes);        /* blocks until dst is valid    */
 int mt_h2d_async(void* dst, const void* pinned_src, size_t bytes);
 int mt_d2h_async(void* pinned_dst, const void* src, size_t bytes);
+/* double-buffered input pipeline: upload on a copy stream while the compute stream works; the copy is ordered
+ * after everything queued on the compute stream at the time of the call (the destination may be a recycled
+ * block), mt_prefetch_wait() orders the compute stream after all prefetches issued so far.              */
+int mt_h2d_prefetch(void* dst, const void* pinned_src, size_t bytes);
+int mt_prefetch_wait(void);
 int mt_d2d(void* dst, const void* src, size_t bytes);
 /* replaces: zeros_like + grad.fill(0.0) (tensor.py:77-85,243-248; module.py:83-89)      */
 int mt_memset_zero(void* ptr, size_t bytes);

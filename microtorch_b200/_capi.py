@@ -39,6 +39,10 @@ PROTOTYPES = {
     "mt_event_destroy": [VP],
     "mt_launch_count": [c_u64p],
     "mt_launch_count_reset": [],
+    "mt_graph_begin": [],
+    "mt_graph_end": [c_voidpp],
+    "mt_graph_launch": [VP],
+    "mt_graph_destroy": [VP],
     "mt_l2_flush": [],
     "mt_prof_enable": [C.c_int],
     "mt_prof_reset": [],
@@ -53,6 +57,8 @@ PROTOTYPES = {
     "mt_d2h": [VP, VP, C.c_size_t],
     "mt_h2d_async": [VP, VP, C.c_size_t],
     "mt_d2h_async": [VP, VP, C.c_size_t],
+    "mt_h2d_prefetch": [VP, VP, C.c_size_t],
+    "mt_prefetch_wait": [],
     "mt_d2d": [VP, VP, C.c_size_t],
     "mt_memset_zero": [VP, C.c_size_t],
     "mt_memset_multi": [c_voidpp, c_sizep, C.c_int],

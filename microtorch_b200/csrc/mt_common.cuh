@@ -26,6 +26,8 @@ struct Global {
   size_t l2_bytes = 0;
   cudaStream_t stream = nullptr;       // compute stream
   cudaStream_t comm_stream = nullptr;  // collective stream
+  cudaStream_t copy_stream = nullptr;  // host->device prefetch stream
+  cudaEvent_t ev_copy = nullptr, ev_copy_gate = nullptr;
   cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
   uint64_t launches = 0;
   int gemm_engine_force = -1;

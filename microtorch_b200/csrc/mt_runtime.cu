@@ -35,12 +35,20 @@ int fail(int status, const char* fmt, ...) {
 // queued earlier on the same stream than whatever the new owner queues ("stream-ordered
 // reuse").  The communication stream only touches gradient buffers that stay owned across
 // the collective (mt_comm_wait orders them back).
+struct Block {
+  size_t size = 0;
+  int graph = 0;       // 0: ordinary block; g > 0: allocated while graph g was being captured
+  bool held = true;    // the caller still owns it (not yet passed to mt_free)
+};
 struct Pool {
   std::mutex mu;
-  std::multimap<size_t, void*> free_blocks;  // rounded size -> block
-  std::map<void*, size_t> live;              // block -> rounded size
+  std::multimap<size_t, void*> free_blocks;  // rounded size -> block (general cache)
+  std::multimap<size_t, void*> cap_free;     // freed during the current capture: reusable only inside it
+  std::map<void*, Block> blocks;             // every block handed out and not yet back in the general cache
   size_t reserved = 0, in_use = 0, peak = 0;
   uint64_t n_req = 0, n_dev = 0;
+  int capturing = 0;                         // id of the graph being captured (0 = none)
+  int next_graph = 1;
 };
 static Pool& pool() {
   static Pool P;
@@ -53,45 +61,57 @@ static size_t round_size(size_t b) {
   return (b + ((2u << 20) - 1)) & ~size_t((2u << 20) - 1);       // 2 MiB classes above
 }
 
+static bool take_cached(std::multimap<size_t, void*>& cache, size_t want, void** p, size_t* sz) {
+  auto it = cache.lower_bound(want);
+  // accept a cached block up to 12.5% larger (bounded internal fragmentation)
+  if (it == cache.end() || it->first > want + want / 8) return false;
+  *p = it->second;
+  *sz = it->first;
+  cache.erase(it);
+  return true;
+}
+
 int pool_alloc(void** out, size_t bytes) {
   Pool& P = pool();
   std::lock_guard<std::mutex> lk(P.mu);
   const size_t want = round_size(bytes);
   P.n_req++;
-  auto it = P.free_blocks.lower_bound(want);
-  // accept a cached block up to 12.5% larger (bounded internal fragmentation)
-  if (it != P.free_blocks.end() && it->first <= want + want / 8) {
-    void* p = it->second;
-    size_t sz = it->first;
-    P.free_blocks.erase(it);
-    P.live[p] = sz;
-    P.in_use += sz;
-    if (P.in_use > P.peak) P.peak = P.in_use;
-    *out = p;
-    return MT_OK;
-  }
   void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, want);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    // release every cached block and retry once
-    cudaStreamSynchronize(g().stream);
-    for (auto& kv : P.free_blocks) {
-      cudaFree(kv.second);
-      P.reserved -= kv.first;
-    }
-    P.free_blocks.clear();
-    e = cudaMalloc(&p, want);
+  size_t sz = 0;
+  // A block used inside a captured graph is written again on every replay, so it stays with that graph: blocks
+  // freed during the capture are recycled only within it, and never return to the general cache before
+  // mt_graph_destroy.
+  bool hit = P.capturing ? take_cached(P.cap_free, want, &p, &sz) : false;
+  if (!hit) hit = take_cached(P.free_blocks, want, &p, &sz);
+  if (!hit) {
+    cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      return fail(MT_ERR_OOM, "mt_malloc: cudaMalloc(%zu) failed: %s (reserved %zu, in use %zu)", want,
-                  cudaGetErrorString(e), P.reserved, P.in_use);
+      if (!P.capturing) {   // release every cached block and retry once
+        cudaStreamSynchronize(g().stream);
+        for (auto& kv : P.free_blocks) {
+          cudaFree(kv.second);
+          P.reserved -= kv.first;
+        }
+        P.free_blocks.clear();
+        e = cudaMalloc(&p, want);
+      }
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MT_ERR_OOM, "mt_malloc: cudaMalloc(%zu) failed: %s (reserved %zu, in use %zu)", want,
+                    cudaGetErrorString(e), P.reserved, P.in_use);
+      }
     }
+    P.n_dev++;
+    P.reserved += want;
+    sz = want;
   }
-  P.n_dev++;
-  P.reserved += want;
-  P.live[p] = want;
-  P.in_use += want;
+  Block b;
+  b.size = sz;
+  b.graph = P.capturing;
+  b.held = true;
+  P.blocks[p] = b;
+  P.in_use += sz;
   if (P.in_use > P.peak) P.peak = P.in_use;
   *out = p;
   return MT_OK;
@@ -101,13 +121,51 @@ int pool_free(void* p) {
   if (!p) return MT_OK;
   Pool& P = pool();
   std::lock_guard<std::mutex> lk(P.mu);
-  auto it = P.live.find(p);
-  if (it == P.live.end()) return fail(MT_ERR_INVALID, "mt_free: %p was not allocated by mt_malloc", p);
-  size_t sz = it->second;
-  P.live.erase(it);
-  P.in_use -= sz;
-  P.free_blocks.emplace(sz, p);
+  auto it = P.blocks.find(p);
+  if (it == P.blocks.end() || !it->second.held)
+    return fail(MT_ERR_INVALID, "mt_free: %p was not allocated by mt_malloc (or freed twice)", p);
+  Block& b = it->second;
+  P.in_use -= b.size;
+  if (b.graph == 0) {
+    P.free_blocks.emplace(b.size, p);
+    P.blocks.erase(it);
+  } else {
+    b.held = false;                                        // stays reserved for its graph
+    if (P.capturing == b.graph) P.cap_free.emplace(b.size, p);
+  }
   return MT_OK;
+}
+
+// graph support (mt_graph_* below)
+static int pool_begin_capture() {
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  if (P.capturing) return 0;
+  P.capturing = P.next_graph++;
+  P.cap_free.clear();
+  return P.capturing;
+}
+static void pool_end_capture() {
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.capturing = 0;
+  P.cap_free.clear();
+}
+static void pool_release_graph(int graph) {
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  for (auto it = P.blocks.begin(); it != P.blocks.end();) {
+    Block& b = it->second;
+    if (b.graph == graph) {
+      if (!b.held) {                                       // already freed by its owner: back to the general cache
+        P.free_blocks.emplace(b.size, it->first);
+        it = P.blocks.erase(it);
+        continue;
+      }
+      b.graph = 0;                                         // still owned by the caller: becomes an ordinary block
+    }
+    ++it;
+  }
 }
 
 }  // namespace mt
@@ -155,6 +213,9 @@ MT_API int mt_init(int device) {
   G.l2_bytes = (size_t)prop.l2CacheSize;
   MT_CUDA(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
   MT_CUDA(cudaStreamCreateWithFlags(&G.comm_stream, cudaStreamNonBlocking));
+  MT_CUDA(cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking));
+  MT_CUDA(cudaEventCreateWithFlags(&G.ev_copy, cudaEventDisableTiming));
+  MT_CUDA(cudaEventCreateWithFlags(&G.ev_copy_gate, cudaEventDisableTiming));
   MT_CUDA(cudaEventCreateWithFlags(&G.ev_compute, cudaEventDisableTiming));
   MT_CUDA(cudaEventCreateWithFlags(&G.ev_comm, cudaEventDisableTiming));
   G.launches = 0;
@@ -173,6 +234,9 @@ MT_API int mt_shutdown(void) {
   cudaEventDestroy(G.ev_comm);
   cudaStreamDestroy(G.stream);
   cudaStreamDestroy(G.comm_stream);
+  cudaStreamDestroy(G.copy_stream);
+  cudaEventDestroy(G.ev_copy);
+  cudaEventDestroy(G.ev_copy_gate);
   G.ready = false;
   return MT_OK;
 }
@@ -196,6 +260,7 @@ MT_API int mt_sync(void) {
   MT_REQUIRE_INIT();
   MT_CUDA(cudaStreamSynchronize(g().stream));
   MT_CUDA(cudaStreamSynchronize(g().comm_stream));
+  MT_CUDA(cudaStreamSynchronize(g().copy_stream));
   return MT_OK;
 }
 
@@ -281,6 +346,78 @@ MT_API int mt_pool_trim(void) {
   return MT_OK;
 }
 
+// ------------------------------------------------------------------ CUDA graphs
+// Capture every launch the library makes between begin and end into one graph: a whole training step becomes a
+// single cudaGraphLaunch (the launch-latency-bound spiral demo runs ~14 tiny kernels per step).
+struct GraphHandle {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int pool_id = 0;
+};
+
+MT_API int mt_graph_begin(void) {
+  MT_REQUIRE_INIT();
+  const int id = pool_begin_capture();
+  if (!id) return fail(MT_ERR_INVALID, "mt_graph_begin: a capture is already in progress");
+  cudaError_t e = cudaStreamBeginCapture(g().stream, cudaStreamCaptureModeRelaxed);
+  if (e != cudaSuccess) {
+    pool_end_capture();
+    pool_release_graph(id);
+    return fail(MT_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+  }
+  return MT_OK;
+}
+
+MT_API int mt_graph_end(void** handle) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(handle, "mt_graph_end: null out pointer");
+  const int id = pool().capturing;
+  if (!id) return fail(MT_ERR_INVALID, "mt_graph_end: no capture in progress");
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(g().stream, &graph);
+  pool_end_capture();
+  if (e != cudaSuccess || !graph) {
+    cudaGetLastError();
+    pool_release_graph(id);
+    return fail(MT_ERR_CUDA, "cudaStreamEndCapture: %s (a blocking call - upload, download, sync - inside the captured "
+                "region invalidates the capture)", cudaGetErrorString(e));
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  if (e != cudaSuccess) {
+    cudaGraphDestroy(graph);
+    pool_release_graph(id);
+    return fail(MT_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  }
+  GraphHandle* h = new GraphHandle;
+  h->graph = graph;
+  h->exec = exec;
+  h->pool_id = id;
+  *handle = h;
+  return MT_OK;
+}
+
+MT_API int mt_graph_launch(void* handle) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(handle, "mt_graph_launch: null handle");
+  MT_CUDA(cudaGraphLaunch(((GraphHandle*)handle)->exec, g().stream));
+  g().launches++;
+  return MT_OK;
+}
+
+MT_API int mt_graph_destroy(void* handle) {
+  if (!handle) return MT_OK;
+  GraphHandle* h = (GraphHandle*)handle;
+  if (g().ready) {
+    cudaStreamSynchronize(g().stream);
+    cudaGraphExecDestroy(h->exec);
+    cudaGraphDestroy(h->graph);
+  }
+  pool_release_graph(h->pool_id);
+  delete h;
+  return MT_OK;
+}
+
 MT_API int mt_host_alloc(void** p, size_t bytes) {
   MT_REQUIRE_INIT();
   MT_CHECK_ARG(p, "mt_host_alloc: null out pointer");
@@ -317,6 +454,26 @@ MT_API int mt_d2h_async(void* dst, const void* src, size_t bytes) {
   MT_REQUIRE_INIT();
   if (!bytes) return MT_OK;
   MT_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g().stream));
+  return MT_OK;
+}
+// Upload on the copy stream so that the NEXT step's inputs travel while the current step computes.
+// The destination may be a recycled pool block that kernels already queued on the compute stream still read,
+// so the copy is gated behind the compute stream's position AT THE TIME OF THIS CALL (issue it before launching
+// the step that should overlap it).  mt_prefetch_wait() then orders the compute stream after all prefetches.
+MT_API int mt_h2d_prefetch(void* dst, const void* pinned_src, size_t bytes) {
+  MT_REQUIRE_INIT();
+  if (!bytes) return MT_OK;
+  Global& G = g();
+  MT_CUDA(cudaEventRecord(G.ev_copy_gate, G.stream));
+  MT_CUDA(cudaStreamWaitEvent(G.copy_stream, G.ev_copy_gate, 0));
+  MT_CUDA(cudaMemcpyAsync(dst, pinned_src, bytes, cudaMemcpyHostToDevice, G.copy_stream));
+  return MT_OK;
+}
+MT_API int mt_prefetch_wait(void) {
+  MT_REQUIRE_INIT();
+  Global& G = g();
+  MT_CUDA(cudaEventRecord(G.ev_copy, G.copy_stream));
+  MT_CUDA(cudaStreamWaitEvent(G.stream, G.ev_copy, 0));
   return MT_OK;
 }
 MT_API int mt_d2d(void* dst, const void* src, size_t bytes) {

@@ -42,6 +42,37 @@ def array(data, dtype=float32) -> DeviceArray:
 asarray = array
 
 
+def pinned_empty(shape, dtype=float32) -> "_np.ndarray":
+    """A NumPy array backed by page-locked host memory (mt_host_alloc): the staging buffer of an input pipeline.
+    The memory is released when the array is garbage-collected."""
+    import ctypes as C
+    import weakref
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    nbytes = int(_np.prod(shape, dtype=_np.int64)) * _np.dtype(dtype).itemsize
+    _capi.require_device()
+    p = C.c_void_p()
+    _capi.check(_capi.lib().mt_host_alloc(C.byref(p), max(nbytes, 1)), "mt_host_alloc")
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = _np.frombuffer(buf, dtype=dtype, count=int(_np.prod(shape, dtype=_np.int64))).reshape(shape)
+    weakref.finalize(buf, _capi.lib().mt_host_free, p.value)
+    return arr
+
+
+def prefetch(host_pinned) -> DeviceArray:
+    """Start uploading a pinned float32 host array on the copy stream and return its DeviceArray at once.
+    Call `wait_prefetch()` before the first kernel that reads it.  Issue the prefetch of batch i+1 BEFORE launching
+    step i: the copy then overlaps step i's compute (see mt_h2d_prefetch in the C header)."""
+    host = _np.ascontiguousarray(host_pinned, dtype=_np.float32)
+    out = DeviceArray.empty(host.shape)
+    if host.nbytes:
+        _capi.check(_capi.lib().mt_h2d_prefetch(out.ptr, host.ctypes.data, host.nbytes), "mt_h2d_prefetch")
+    return out
+
+
+def wait_prefetch() -> None:
+    _capi.check(_capi.lib().mt_prefetch_wait(), "mt_prefetch_wait")
+
+
 def zeros_like(x, dtype=None) -> DeviceArray:
     return DeviceArray.zeros(x.shape)
 

@@ -381,3 +381,30 @@ def test_c3_sweep_properties_large(mt):
     np.testing.assert_allclose(host(y.grad), np.full((1, 4096), 0.75 * (n // 4096)), rtol=1e-5)
     m = x.mean()
     assert abs(m.item() - 0.75) <= 1e-5
+
+
+def test_graphed_training_step_matches_eager_and_notebook(mt):
+    """Whole-step CUDA graph (section 8f #1): 101 replays of the captured spiral-demo step reproduce the eager loss
+    stream bit for bit and the notebook's published stream to 1e-5; parameters end identical to the eager run."""
+    from microtorch_b200.graph import GraphedStep
+    from microtorch_b200.trainer import train_step
+    wl = W.C1A
+    pub = json.load(open(os.path.join(GOLDEN, "c1a_notebook_losses.json")))["losses"]
+    eager = run_cuda(mt, wl, 104)
+
+    model, x, t = W.setup(wl, mt.Linear, mt.Tanh, mt.Sequential)
+    X, T = mt.Tensor(x, device="cuda"), mt.Tensor(t, device="cuda")
+    loss_fn, opt = mt.losses[wl.loss](), mt.SGD(model.parameters, lr=wl.lr)
+    losses = []
+    step = GraphedStep(lambda: train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim), warmup=2)
+    # warm-up ran 2 eager steps, the capture itself does not execute: the first replay is step 2
+    for _ in range(102):
+        step.replay()
+        losses.append(step.result.item())
+    got = np.array(losses, np.float32)
+    np.testing.assert_array_equal(got, eager["losses"][2:104])
+    want = np.array([float(pub[str(i)]) for i in range(2, 102)], dtype=np.float32)
+    np.testing.assert_allclose(got[:100], want, rtol=1e-5)
+    for p, q in zip(model.parameters(), eager["params"]):
+        np.testing.assert_array_equal(host(p.data), q)
+    step.close()

@@ -85,13 +85,36 @@ def main():
         print(json.dumps({"config": tag + "_cpu_oracle", "ms_per_step": dt * 1e3, "samples_per_s": wl.batch / dt,
                           "host_cpus": os.cpu_count()}), flush=True)
 
+    def run_graphed(wl, steps, tag):
+        from microtorch_b200.graph import GraphedStep
+        model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+        X, T = Tensor(x, device="cuda"), Tensor(t, device="cuda")
+        loss_fn, opt = losses[wl.loss](), SGD(model.parameters, lr=wl.lr)
+        g = GraphedStep(lambda: train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim), warmup=3)
+        for _ in range(20):
+            g.replay()
+        lib.mt_sync()
+        lib.mt_event_record(e0)
+        for _ in range(steps):
+            g.replay()
+        lib.mt_event_record(e1)
+        lib.mt_event_sync(e1)
+        ms = C.c_float()
+        lib.mt_event_elapsed_ms(e0, e1, C.byref(ms))
+        print(json.dumps({"config": tag + "_cuda_graph", "steps": steps, "ms_per_step": ms.value / steps,
+                          "steps_per_s": steps / (ms.value / 1e3), "samples_per_s": wl.batch * steps / (ms.value / 1e3),
+                          "last_loss": g.result.item()}), flush=True)
+        g.close()
+
     want = lambda k: (not args.only) or k in args.only.split(",")
     if want("c1a"):
         run(W.C1A, 2000, 50, "c1a_spiral_notebook_mlp_2_64_32_16_1")
+        run_graphed(W.C1A, 5000, "c1a_spiral_notebook_mlp_2_64_32_16_1")
         if args.cpu:
             cpu(W.C1A, 500, "c1a")
     if want("c1b"):
         run(W.C1B, 2000, 50, "c1b_spiral_2_100_3")
+        run_graphed(W.C1B, 5000, "c1b_spiral_2_100_3")
         if args.cpu:
             cpu(W.C1B, 500, "c1b")
     if want("c4"):

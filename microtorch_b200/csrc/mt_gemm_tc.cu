@@ -856,6 +856,9 @@ int gemm_tc_try(const GemmArgs& a) {
   // worthwhile shapes only: small / skinny problems are SIMT territory (HBM- or latency-bound)
   if (g().gemm_engine_force != 1) {
     if (a.M < 128 || a.N < 64 || a.K < 32) return MT_ERR_UNSUPPORTED;
+    // below ~16 M multiply-adds the 512-thread / 227 KB / TMEM kernel is pure launch latency (14 us measured on the
+    // 200x64x32 spiral-demo layers): the SIMT tile finishes sooner
+    if (a.M * a.N * a.K < (1ll << 24)) return MT_ERR_UNSUPPORTED;
   } else if (a.M < 1 || a.N < 4 || a.K < 1) {
     return MT_ERR_UNSUPPORTED;
   }

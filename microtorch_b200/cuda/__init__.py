@@ -51,8 +51,9 @@ def pinned_empty(shape, dtype=float32) -> "_np.ndarray":
     nbytes = int(_np.prod(shape, dtype=_np.int64)) * _np.dtype(dtype).itemsize
     _capi.require_device()
     p = C.c_void_p()
-    _capi.check(_capi.lib().mt_host_alloc(C.byref(p), max(nbytes, 1)), "mt_host_alloc")
-    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    nalloc = nbytes if nbytes > 0 else 1        # (`max`/`min` in this namespace are the NumPy-API stubs below)
+    _capi.check(_capi.lib().mt_host_alloc(C.byref(p), nalloc), "mt_host_alloc")
+    buf = (C.c_char * nalloc).from_address(p.value)
     arr = _np.frombuffer(buf, dtype=dtype, count=int(_np.prod(shape, dtype=_np.int64))).reshape(shape)
     weakref.finalize(buf, _capi.lib().mt_host_free, p.value)
     return arr

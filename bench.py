@@ -101,7 +101,7 @@ def ncu_traffic_per_launch():
     """dram__bytes_read+write per GEMM launch from the committed `ncu --set full` capture, or None."""
     import csv
     import glob
-    paths = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_gemm_ncu_full_summary.csv")))
+    paths = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_gemm_ncu_full_summary*.csv")))
     if not paths:
         return None
     try:

@@ -7,28 +7,30 @@
 //
 // 3xTF32 split done ON CHIP: x = hi + lo with hi = tf32(x), lo = tf32(x - hi);
 //   A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi   (lo.lo ~ 2^-22 is dropped), fp32 accumulate in TMEM.
-// No split copies ever touch HBM: TMA lands the raw fp32 tile in shared memory, four
-// "converter" warps rewrite it in place as hi and write lo to a twin buffer with the SAME
-// (swizzled) layout - the conversion is element-wise on the byte image, so it is independent of
-// the swizzle - then hand the stage to the single MMA-issuing thread.  The backward prologue
-// dZ = dY * (1 - Y^2) is fused into the same pass (the Y tile is TMA-loaded into the lo buffer).
+// No split copies ever touch HBM: TMA lands the raw fp32 tile in shared memory - the tensor core truncates it
+// to TF32 itself, so the raw tile IS hi - and four "converter" warps write lo to a second buffer with the SAME
+// (swizzled) layout: the conversion is element-wise on the byte image, so it is independent of the swizzle.
+// The optional backward prologue dZ = dY * (1 - Y^2) is fused into the same pass (the Y tile rides in the raw
+// stage); for large problems the tanh' factor is applied in the PRODUCING GEMM's epilogue instead (epi_tanh).
 //
-// CTA = 16 warps (4 warpgroups), persistent over output tiles (grid = #SMs), 128 x BN x 32 tiles:
-//   warp 0      TMA producer      (one lane)            full[s]  <- bytes landed
-//   warp 1      MMA issuer        (one lane) + TMEM     empty[s] <- tcgen05.commit, tfull[a] <- chunk done
-//   warps 4-7   converters        (128 threads)         conv[s]  <- hi/lo ready (generic->async proxy fence)
-//   warps 8-15  accumulate/epilogue (256 threads)       tempty[a] <- accumulator drained
+// Persistent grid: one CTA PAIR (cluster of 2, tcgen05 cta_group::2) per two SMs loops over 256 x 256 output tiles
+// (single CTAs, 128 x 128 tiles, when N <= 128).  Each CTA = 16 warps in 4 warpgroups:
+//   warp 0      TMA producer      (one lane)            full[r]  <- bytes landed (own A rows, own half of B)
+//   warps 4-7   converters        (128 threads)         conv[l]  <- hi/lo ready, arrives on the LEADER's barrier
+//   warp 1      MMA issuer        (leader CTA, 1 lane)  empty[r], lofree[l], tfull[a] <- tcgen05.commit multicast
+//   warps 8-15  accumulate/epilogue (256 threads)       tempty[a] <- accumulator drained (leader's barrier)
+// Two shared-memory rings: a deep raw ring (TMA destination) and a shallow lo ring (converter output).
 // The tensor core adds into its fp32 TMEM accumulator with truncation (measured: error grows
 // linearly, ~2^-24 per tcgen05.mma, 7.5e-5 at K=4096), so K is cut into chunks of CHUNK_KB
 // k-blocks: each chunk accumulates into one of two TMEM buffers (ping-pong) and the epilogue
 // warps fold finished chunks into IEEE fp32 running sums held in registers (setmaxnreg gives
 // them 200 registers, the data-movement warps 56).  Chunk c+1's MMAs overlap chunk c's drain
-// and the previous tile's bias/tanh/store epilogue.
+// and the previous tile's bias/tanh/store epilogue.  DESIGN.md section 4.1 has the measurements behind each choice.
 // Operands may be K-major or MN-major (UMMA descriptor transpose bits), so forward (X.W^T), dX
 // (dZ.W) and dW (dZ^T.X) all read the row-major activations/weights in place - no transposes.
 //
-// Roofline: tensor pipe.  One k-block (32) of a 128x256 tile is 12 tcgen05.mma (M128 N256 K8),
-// 128 cycles each; the logical 2*M*N*K flops are reported against (TF32 dense peak)/3.
+// Roofline: tensor pipe (91-99 % active in the ncu captures under profiles/).  One k-block (32) of a 256x256 pair
+// tile is 12 tcgen05.mma (M256 N256 K8), 128 cycles each; logical 2*M*N*K flops are reported against (TF32 peak)/3.
 #include <cuda.h>
 
 #include <algorithm>
@@ -106,24 +108,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -263,7 +247,6 @@ struct Params {
   int act, accumulate;
   int m_blocks, n_blocks, k_blocks;
   int chunk_kb;       // k-blocks accumulated in TMEM before a flush to the fp32 register sums
-  int has_prologue;   // A' = A * (1 - T^2)
   int write_hi;       // converters store hi explicitly (else the MMA's own truncation of the raw fp32 is hi)
   int splits, kb_per_split;    // split-K: work item = (tile, split); split s covers k-blocks [s*kbps, (s+1)*kbps)
                                // and writes its partial to C + s*M*N (folded by splitk_finalize)
@@ -733,7 +716,6 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   p.n_blocks = (int)ceil_div(a.N, BN);
   p.k_blocks = (int)ceil_div(a.K, BK);
   p.chunk_kb = g_chunk_kb > 0 ? g_chunk_kb : p.k_blocks;
-  p.has_prologue = a.tanh_src ? 1 : 0;
   p.write_hi = g_write_hi;
   p.dbg = g_dbg_flags;
   {  // ring depths: lo ring g_lo_stages deep (default 3), raw ring takes the rest of the 227 KB

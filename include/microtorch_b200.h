@@ -132,7 +132,12 @@ typedef enum mt_binary_op {
   MT_BIN_DIV = 3,       /* a / b            math.py:12 (log backward g / x)                    */
   MT_BIN_TANH_BWD = 4,  /* a * (1 - b*b)    math.py:74   a = grad, b = saved tanh OUTPUT       */
   MT_BIN_POW_BWD = 5,   /* a * (p * b**(p-1))  math.py:51   a = grad, b = saved input, p = scalar */
-  MT_BIN_EXP_BWD = 6    /* a * b            math.py:31   a = grad, b = saved exp output        */
+  MT_BIN_EXP_BWD = 6,   /* a * b            math.py:31   a = grad, b = saved exp output        */
+  /* comparison / select family (src/tensor/tensor.py:514-536, src/tensor/ops/elementwise.py): results are
+   * float32 masks 1.0 / 0.0 ON THE DEVICE (the reference builds CPU tensors here and cannot run them under CuPy, Q8) */
+  MT_BIN_LT = 7, MT_BIN_GT = 8, MT_BIN_LE = 9, MT_BIN_GE = 10, MT_BIN_EQ = 11, MT_BIN_NE = 12,
+  MT_BIN_MAX = 13,      /* max(a, b)        tensor.py:291 clip lower bound                     */
+  MT_BIN_MIN = 14       /* min(a, b)        tensor.py:291 clip upper bound                     */
 } mt_binary_op;
 
 /* out[idx] = op(a[idx . a_strides], b[idx . b_strides]) over the broadcast `shape`;
@@ -153,9 +158,17 @@ typedef enum mt_unary_op {
   MT_UN_EXP = 3,        /* exp x       math.py:27                   */
   MT_UN_POW = 4,        /* x ** s      math.py:47 (NumPy fast paths for s in {-1,0,0.5,1,2}) */
   MT_UN_SCALE = 5,      /* x * s       optimizer.py:39 (lr * grad); tensor.py:310            */
-  MT_UN_ADDS = 6        /* x + s                                                            */
+  MT_UN_ADDS = 6,       /* x + s                                                            */
+  MT_UN_ABS = 7         /* |x|                                                              */
 } mt_unary_op;
 int mt_ew_unary_f32(int op, float* out, const float* x, size_t n, float scalar);
+
+/* out[idx] = cond[idx . c_strides] != 0 ? a[idx . a_strides] : b[idx . b_strides]   (out contiguous)
+ * replaces: tnsr.where(condition.data, a.data, b.data) and its two backward selects
+ * (src/tensor/ops/elementwise.py:10,16,21)                                                */
+int mt_ew_where_f32(float* out, const float* cond, const float* a, const float* b, int ndim,
+                    const int64_t* shape, const int64_t* c_strides, const int64_t* a_strides,
+                    const int64_t* b_strides);
 
 /* ---------------------------------------------------------------- reductions ------ */
 /* x viewed as [outer, red, inner] (contiguous); out[o,i] = sum_r x[o,r,i] * w[o,r,i]

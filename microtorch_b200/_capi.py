@@ -70,6 +70,7 @@ PROTOTYPES = {
     "mt_ew_binary_f32": [C.c_int, VP, VP, VP, C.c_int, c_i64p, c_i64p, c_i64p, C.c_float],
     "mt_ew_inplace_f32": [C.c_int, VP, c_i64p, VP, c_i64p, C.c_int, c_i64p],
     "mt_ew_unary_f32": [C.c_int, VP, VP, C.c_size_t, C.c_float],
+    "mt_ew_where_f32": [VP, VP, VP, VP, C.c_int, c_i64p, c_i64p, c_i64p, c_i64p],
     "mt_reduce_sum_f32": [VP, VP, C.c_int64, C.c_int64, C.c_int64, VP, C.c_int64, C.c_int64, C.c_int64],
     "mt_linear_fwd_f32": [VP, VP, VP, VP, C.c_int64, C.c_int64, C.c_int64, C.c_int],
     "mt_linear_bwd_f32": [VP, VP, VP, VP, VP, VP, C.c_int64, C.c_int64, C.c_int64, C.c_int],
@@ -91,7 +92,8 @@ STRING_FUNCS = ("mt_last_error", "mt_version")
 
 # enums of the header
 BIN_ADD, BIN_MUL, BIN_SUB, BIN_DIV, BIN_TANH_BWD, BIN_POW_BWD, BIN_EXP_BWD = range(7)
-UN_NEG, UN_LOG, UN_TANH, UN_EXP, UN_POW, UN_SCALE, UN_ADDS = range(7)
+BIN_LT, BIN_GT, BIN_LE, BIN_GE, BIN_EQ, BIN_NE, BIN_MAX, BIN_MIN = range(7, 15)
+UN_NEG, UN_LOG, UN_TANH, UN_EXP, UN_POW, UN_SCALE, UN_ADDS, UN_ABS = range(8)
 ACT_NONE, ACT_TANH = 0, 1
 LOSS_MSE, LOSS_CE_REF, LOSS_BCE = 0, 1, 2
 

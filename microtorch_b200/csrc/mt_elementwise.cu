@@ -41,6 +41,14 @@ __device__ __forceinline__ float bin_op(float a, float b, float s) {
   if (OP == MT_BIN_TANH_BWD) return __fmul_rn(a, __fsub_rn(1.f, __fmul_rn(b, b)));
   if (OP == MT_BIN_POW_BWD) return __fmul_rn(a, __fmul_rn(s, np_pow(b, s - 1.f)));
   if (OP == MT_BIN_EXP_BWD) return __fmul_rn(a, b);
+  if (OP == MT_BIN_LT) return a < b ? 1.f : 0.f;
+  if (OP == MT_BIN_GT) return a > b ? 1.f : 0.f;
+  if (OP == MT_BIN_LE) return a <= b ? 1.f : 0.f;
+  if (OP == MT_BIN_GE) return a >= b ? 1.f : 0.f;
+  if (OP == MT_BIN_EQ) return a == b ? 1.f : 0.f;
+  if (OP == MT_BIN_NE) return a != b ? 1.f : 0.f;
+  if (OP == MT_BIN_MAX) return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);   // NumPy propagates NaN
+  if (OP == MT_BIN_MIN) return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b);
   return 0.f;
 }
 
@@ -53,6 +61,7 @@ __device__ __forceinline__ float un_op(float x, float s) {
   if (OP == MT_UN_POW) return np_pow(x, s);
   if (OP == MT_UN_SCALE) return __fmul_rn(x, s);
   if (OP == MT_UN_ADDS) return __fadd_rn(x, s);
+  if (OP == MT_UN_ABS) return fabsf(x);
   return 0.f;
 }
 
@@ -208,6 +217,48 @@ __global__ void __launch_bounds__(THREADS) unary_kernel(float* __restrict__ out,
   for (size_t j = (n4 << 2) + tid; j < n; j += stride) out[j] = un_op<OP>(x[j], s);
 }
 
+// ---- where(cond, a, b): dense fast path (all three operands contiguous) and a strided general path
+__global__ void __launch_bounds__(THREADS) where_flat_kernel(float* __restrict__ out, const float* __restrict__ c,
+                                                             const float* __restrict__ a, const float* __restrict__ b,
+                                                             size_t n, int vec_ok) {
+  const size_t tid = (size_t)blockIdx.x * THREADS + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * THREADS;
+  const size_t n4 = vec_ok ? (n >> 2) : 0;
+  for (size_t i = tid; i < n4; i += stride) {
+    const float4 vc = mtd::ld_stream4(c + 4 * i), va = mtd::ld_stream4(a + 4 * i), vb = mtd::ld_stream4(b + 4 * i);
+    float4 r;
+    r.x = vc.x != 0.f ? va.x : vb.x;
+    r.y = vc.y != 0.f ? va.y : vb.y;
+    r.z = vc.z != 0.f ? va.z : vb.z;
+    r.w = vc.w != 0.f ? va.w : vb.w;
+    mtd::st4(out + 4 * i, r);
+  }
+  for (size_t j = (n4 << 2) + tid; j < n; j += stride) out[j] = c[j] != 0.f ? a[j] : b[j];
+}
+
+struct Nd3Desc {
+  int ndim;
+  long long shape[MT_MAX_DIMS];
+  long long sc[MT_MAX_DIMS], sa[MT_MAX_DIMS], sb[MT_MAX_DIMS];
+};
+__global__ void __launch_bounds__(THREADS) where_nd_kernel(float* __restrict__ out, const float* __restrict__ c,
+                                                           const float* __restrict__ a, const float* __restrict__ b,
+                                                           const __grid_constant__ Nd3Desc d, long long total) {
+  const long long stride = (long long)gridDim.x * THREADS;
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < total; i += stride) {
+    long long rem = i, oc = 0, oa = 0, ob = 0;
+#pragma unroll 1
+    for (int k = d.ndim - 1; k >= 0; --k) {
+      long long q = rem / d.shape[k], x = rem - q * d.shape[k];
+      oc += x * d.sc[k];
+      oa += x * d.sa[k];
+      ob += x * d.sb[k];
+      rem = q;
+    }
+    out[i] = c[oc] != 0.f ? a[oa] : b[ob];
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // drop extent-1 dims and merge neighbours that are contiguous for BOTH operands
@@ -310,6 +361,14 @@ MT_API int mt_ew_binary_f32(int op, float* out, const float* a, const float* b, 
     case MT_BIN_TANH_BWD: return launch_binary<MT_BIN_TANH_BWD>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
     case MT_BIN_POW_BWD: return launch_binary<MT_BIN_POW_BWD>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
     case MT_BIN_EXP_BWD: return launch_binary<MT_BIN_EXP_BWD>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
+    case MT_BIN_LT: return launch_binary<MT_BIN_LT>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
+    case MT_BIN_GT: return launch_binary<MT_BIN_GT>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
+    case MT_BIN_LE: return launch_binary<MT_BIN_LE>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
+    case MT_BIN_GE: return launch_binary<MT_BIN_GE>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
+    case MT_BIN_EQ: return launch_binary<MT_BIN_EQ>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
+    case MT_BIN_NE: return launch_binary<MT_BIN_NE>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
+    case MT_BIN_MAX: return launch_binary<MT_BIN_MAX>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
+    case MT_BIN_MIN: return launch_binary<MT_BIN_MIN>(out, a, b, ndim, shape, a_strides, b_strides, scalar);
   }
   return fail(MT_ERR_INVALID, "mt_ew_binary_f32: unknown op %d", op);
 }
@@ -348,6 +407,37 @@ MT_API int mt_ew_inplace_f32(int op, float* dst, const int64_t* dst_strides, con
   return MT_OK;
 }
 
+MT_API int mt_ew_where_f32(float* out, const float* cond, const float* a, const float* b, int ndim, const int64_t* shape,
+                           const int64_t* c_strides, const int64_t* a_strides, const int64_t* b_strides) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(ndim >= 0 && ndim <= MT_MAX_DIMS, "mt_ew_where_f32: ndim %d out of range", ndim);
+  MT_CHECK_ARG(out && cond && a && b, "mt_ew_where_f32: null pointer");
+  long long total = 1, expect = 1;
+  bool dense = true;
+  for (int k = ndim - 1; k >= 0; --k) {
+    total *= shape[k];
+    if (shape[k] != 1 && (c_strides[k] != expect || a_strides[k] != expect || b_strides[k] != expect)) dense = false;
+    expect *= shape[k];
+  }
+  if (total == 0) return MT_OK;
+  if (dense) {
+    const int vec = aligned16(out) && aligned16(cond) && aligned16(a) && aligned16(b);
+    where_flat_kernel<<<ew_grid(total / 4 + 1, THREADS * UNROLL), THREADS, 0, g().stream>>>(out, cond, a, b, (size_t)total, vec);
+  } else {
+    Nd3Desc d;
+    d.ndim = ndim;
+    for (int k = 0; k < ndim; ++k) {
+      d.shape[k] = shape[k];
+      d.sc[k] = c_strides[k];
+      d.sa[k] = a_strides[k];
+      d.sb[k] = b_strides[k];
+    }
+    where_nd_kernel<<<ew_grid(total, THREADS * UNROLL), THREADS, 0, g().stream>>>(out, cond, a, b, d, total);
+  }
+  MT_LAUNCHED();
+  return MT_OK;
+}
+
 MT_API int mt_ew_unary_f32(int op, float* out, const float* x, size_t n, float scalar) {
   MT_REQUIRE_INIT();
   if (n == 0) return MT_OK;
@@ -363,6 +453,7 @@ MT_API int mt_ew_unary_f32(int op, float* out, const float* x, size_t n, float s
     case MT_UN_POW: unary_kernel<MT_UN_POW><<<grid, THREADS, 0, st>>>(out, x, n, scalar, vec); break;
     case MT_UN_SCALE: unary_kernel<MT_UN_SCALE><<<grid, THREADS, 0, st>>>(out, x, n, scalar, vec); break;
     case MT_UN_ADDS: unary_kernel<MT_UN_ADDS><<<grid, THREADS, 0, st>>>(out, x, n, scalar, vec); break;
+    case MT_UN_ABS: unary_kernel<MT_UN_ABS><<<grid, THREADS, 0, st>>>(out, x, n, scalar, vec); break;
     default: return fail(MT_ERR_INVALID, "mt_ew_unary_f32: unknown op %d", op);
   }
   MT_LAUNCHED();

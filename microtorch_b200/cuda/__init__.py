@@ -3,7 +3,7 @@
 It stands where the `cupy` module stands in the reference (src/tensor/device.py:74-84):
 the NumPy-API names the reference calls on the module object, all
 backed by libmicrotorch_b200.so.  Names that the training path never calls on CUDA and
-that the reference's own CuPy path cannot run either (where / comparisons, Q8) raise.
+are not implemented (max / min reductions) raise; comparisons, where, clip, abs and norm run on the device.
 """
 
 from __future__ import annotations
@@ -162,7 +162,45 @@ def _unsupported(name):
     return fn
 
 
-where = _unsupported("where")
-clip = _unsupported("clip")
+def where(cond, a, b):
+    return kernels.where(cond, a, b)
+
+
+def maximum(a, b):
+    return kernels.binary(_capi.BIN_MAX, a, b)
+
+
+def minimum(a, b):
+    return kernels.binary(_capi.BIN_MIN, a, b)
+
+
+def abs(x):                        # noqa: A001
+    return kernels.unary(_capi.UN_ABS, x)
+
+
+def clip(x, lo, hi):
+    out = x
+    if lo is not None:
+        out = kernels.binary(_capi.BIN_MAX, out, float(lo))
+    if hi is not None:
+        out = kernels.binary(_capi.BIN_MIN, out, float(hi))
+    return out
+
+
+class linalg:                      # noqa: N801  (NumPy name)
+    @staticmethod
+    def norm(x, ord=2.0):          # noqa: A002
+        """Vector p-norm of all elements as a host float (the reference compares it on the host, tensor.py:308-309)."""
+        x = _as_device(x)
+        axes = tuple(range(x.ndim))
+        if ord == 2 or ord == 2.0:
+            return float(kernels.reduce_sum(x, axes, x).item()) ** 0.5        # fused x*x reduction
+        if ord == 1 or ord == 1.0:
+            return float(kernels.reduce_sum(kernels.unary(_capi.UN_ABS, x), axes).item())
+        p = float(ord)
+        powed = kernels.unary(_capi.UN_POW, kernels.unary(_capi.UN_ABS, x), p)
+        return float(kernels.reduce_sum(powed, axes).item()) ** (1.0 / p)
+
+
 max = _unsupported("max")          # noqa: A001
 min = _unsupported("min")          # noqa: A001

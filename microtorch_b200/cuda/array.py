@@ -8,8 +8,8 @@ bytes is a C-ABI call; nothing here computes on the CPU.
 
 Surface = the array-object API the reference calls on `tensor.data` / `grad`
 (SURVEY.md Appendix D): shape/ndim/size/dtype/T, reshape, sum, swapaxes, squeeze, astype,
-copy, fill, item, get, __getitem__/__setitem__, + * @ ** / unary -, comparisons are not
-supported on the device (broken in the reference's CuPy path too, Q8).
+copy, fill, item, get, __getitem__/__setitem__, + * @ ** / unary -, and comparisons (float32
+0/1 masks that stay on the device - the reference moves them to the CPU, Q8).
 """
 
 from __future__ import annotations
@@ -394,10 +394,13 @@ class DeviceArray:
         from . import kernels as K
         return K.sum(self, axis, keepdims)
 
-    def _unsupported_compare(self, *_):
-        raise NotImplementedError("comparisons are not implemented on the device (the reference's CuPy path "
-                                  "returns CPU tensors here and cannot work either, SURVEY.md Q8)")
-    __lt__ = __gt__ = __le__ = __ge__ = _unsupported_compare
+    # comparisons: float32 masks (1.0 / 0.0) on the device
+    def __lt__(self, o): from . import kernels as K; return K.binary(_capi.BIN_LT, self, o)
+    def __gt__(self, o): from . import kernels as K; return K.binary(_capi.BIN_GT, self, o)
+    def __le__(self, o): from . import kernels as K; return K.binary(_capi.BIN_LE, self, o)
+    def __ge__(self, o): from . import kernels as K; return K.binary(_capi.BIN_GE, self, o)
+    def __eq__(self, o): from . import kernels as K; return K.binary(_capi.BIN_EQ, self, o)
+    def __ne__(self, o): from . import kernels as K; return K.binary(_capi.BIN_NE, self, o)
     __hash__ = object.__hash__
 
 

@@ -38,6 +38,19 @@ def binary(op: int, a, b, scalar: float = 0.0, out: Optional[DeviceArray] = None
     return out
 
 
+def where(cond, a, b) -> DeviceArray:
+    """cond != 0 ? a : b with NumPy broadcasting (Python scalars allowed for a / b)."""
+    cond, a, b = _as_device(cond), _as_device(a), _as_device(b)
+    shape = broadcast_shape(broadcast_shape(cond.shape, a.shape), b.shape)
+    cv, av, bv = cond.broadcast_to(shape), a.broadcast_to(shape), b.broadcast_to(shape)
+    out = DeviceArray.empty(shape)
+    if out.size:
+        _capi.check(_lib().mt_ew_where_f32(out.ptr, cv.ptr, av.ptr, bv.ptr, len(shape), _capi.i64(shape),
+                                           _capi.i64(cv.strides), _capi.i64(av.strides), _capi.i64(bv.strides)),
+                    "mt_ew_where_f32")
+    return out
+
+
 def inplace(op: int, dst: DeviceArray, src) -> DeviceArray:
     """dst (op)= src, broadcasting src; dst may be a strided view (np.add(a, b, out=a))."""
     src = _as_device(src)

@@ -118,6 +118,9 @@ class CpuBackend:
         full[index] = g
         return full
 
+    @staticmethod
+    def where(c, a, b): return np.where(c, a, b)
+
     # -- grads --------------------------------------------------------------------------
     @staticmethod
     def zeros_like(x, dtype=None): return np.zeros_like(x, dtype=dtype)
@@ -182,6 +185,8 @@ class CudaBackend:
         full = self.ndarray.zeros(like.shape)
         full[index] = g
         return full
+
+    def where(self, c, a, b): return self.K.where(c, a, b)
 
     # -- grads --------------------------------------------------------------------------
     def zeros_like(self, x, dtype=None): return self.ndarray.zeros(x.shape)

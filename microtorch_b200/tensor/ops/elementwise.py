@@ -1,29 +1,22 @@
 """where / maximum / minimum / abs (interface of the reference's src/tensor/ops/elementwise.py).
-CPU only: they are built on comparisons, which the reference evaluates into CPU tensors even
-for CUDA operands, so its CUDA path cannot run them either."""
+
+On CUDA these run on the device: comparisons yield float32 0/1 masks that STAY on the operands' device
+(the reference evaluates them into CPU tensors even for CUDA operands, so its own CUDA path cannot run
+this family - SURVEY.md Q8; fixing that is section 8(f) item 3)."""
 
 from __future__ import annotations
 
-import numpy as np
-
-from ..device import Device
 from ..types import TensorLike, TProps
-from ._tape import record
-
-
-def _cpu_only(*tensors) -> None:
-    for t in tensors:
-        if getattr(t, "device", Device.CPU) != Device.CPU:
-            raise NotImplementedError("where/maximum/minimum/abs are CPU-only (outside the CUDA training path)")
+from ._tape import be, record
 
 
 class Elementwise:
     @staticmethod
     def where(condition: TensorLike, a: TensorLike, b: TensorLike) -> TProps:
-        _cpu_only(condition, a, b)
+        backend = be(a)
         mask = condition.data
-        out = np.where(mask, a.data, b.data)
-        return record(out, a, [(a, lambda g: np.where(mask, g, 0.0)), (b, lambda g: np.where(mask, 0.0, g))])
+        out = backend.where(mask, a.data, b.data)
+        return record(out, a, [(a, lambda g: backend.where(mask, g, 0.0)), (b, lambda g: backend.where(mask, 0.0, g))])
 
     @staticmethod
     def maximum(a: TensorLike, b: TensorLike) -> TProps:

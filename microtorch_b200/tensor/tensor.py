@@ -300,9 +300,7 @@ class Tensor(TensorLike):
 
     def clip_grad_norm(self, max_norm: float = 1.0, norm_type: float = 2.0, eps: float = 1e-6) -> None:
         if self.requires_grad and self.grad is not None:
-            if self.device == Device.CUDA:
-                raise NotImplementedError("clip_grad_norm is not part of the CUDA training path yet")
-            norm = np.linalg.norm(self.grad, norm_type)
+            norm = _tensor(self.device).linalg.norm(self.grad, norm_type)
             if norm > max_norm:
                 self.grad = self.grad * (max_norm / (norm + eps))
 
@@ -409,19 +407,23 @@ class Tensor(TensorLike):
     def abs(self) -> "Tensor":
         return Elementwise.abs(self)
 
+    def _const(self, value) -> "Tensor":
+        """A scalar constant on THIS tensor's device (the reference builds these on the CPU, Q8)."""
+        return data_cast(value, self.device)
+
     def threshold(self, threshold: float, value: float) -> "Tensor":
-        return Tensor.where(self > threshold, self, Tensor(value))
+        return Tensor.where(self > threshold, self, self._const(value))
 
     @input_gate
     def masked_fill(self, mask: "Tensor", value: float) -> "Tensor":
-        return Tensor.where(mask, Tensor(value), self)
+        return Tensor.where(mask, self._const(value), self)
 
     def sign(self) -> "Tensor":
-        return Tensor.where(self > 0, Tensor(1), Tensor.where(self < 0, Tensor(-1), Tensor(0)))
+        return Tensor.where(self > 0, self._const(1), Tensor.where(self < 0, self._const(-1), self._const(0)))
 
     def clip(self, min_value: Optional[float] = None, max_value: Optional[float] = None) -> "Tensor":
-        return Tensor.where(self < min_value, Tensor(min_value),
-                            Tensor.where(self > max_value, Tensor(max_value), self))
+        return Tensor.where(self < min_value, self._const(min_value),
+                            Tensor.where(self > max_value, self._const(max_value), self))
 
     # ------------------------------------------------------------------ indexing / comparisons
     @from_op
@@ -430,27 +432,27 @@ class Tensor(TensorLike):
 
     @data_gate
     def __lt__(self, other: Data) -> "Tensor":
-        return Tensor(self.data < other.data)
+        return Tensor(self.data < other.data, device=self.device)
 
     @data_gate
     def __gt__(self, other: Data) -> "Tensor":
-        return Tensor(self.data > other.data)
+        return Tensor(self.data > other.data, device=self.device)
 
     @data_gate
     def __eq__(self, other: Data) -> "Tensor":
-        return Tensor(self.data == other.data)
+        return Tensor(self.data == other.data, device=self.device)
 
     @data_gate
     def __le__(self, other: Data) -> "Tensor":
-        return Tensor(self.data <= other.data)
+        return Tensor(self.data <= other.data, device=self.device)
 
     @data_gate
     def __ge__(self, other: Data) -> "Tensor":
-        return Tensor(self.data >= other.data)
+        return Tensor(self.data >= other.data, device=self.device)
 
     @data_gate
     def __ne__(self, other: Data) -> "Tensor":
-        return Tensor(self.data != other.data)
+        return Tensor(self.data != other.data, device=self.device)
 
     __hash__ = object.__hash__
 

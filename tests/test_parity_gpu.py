@@ -408,3 +408,73 @@ def test_graphed_training_step_matches_eager_and_notebook(mt):
     for p, q in zip(model.parameters(), eager["params"]):
         np.testing.assert_array_equal(host(p.data), q)
     step.close()
+
+
+def test_select_family_and_l1loss_on_cuda_match_cpu_path(mt):
+    """Section 8(f) item 3: comparisons / where / abs / maximum / minimum / threshold / masked_fill / sign / clip /
+    L1Loss / clip_grad(_norm) on the device, bit-exact against this package's CPU path (which passes the reference's
+    own unit tests for this family).  The reference cannot run these under CuPy at all (Q8)."""
+    from microtorch_b200.nn.loss import L1Loss
+    rng = np.random.default_rng(21)
+    xv = rng.standard_normal((33, 65)).astype(np.float32)
+    yv = rng.standard_normal((33, 65)).astype(np.float32)
+    xv[0, :5] = yv[0, :5]                                                       # ties for == / >=
+
+    def both(fn):
+        outs = []
+        for dev in ("cpu", "cuda"):
+            x = mt.Tensor(xv, requires_grad=True, device=dev)
+            y = mt.Tensor(yv, requires_grad=True, device=dev)
+            r = fn(x, y)
+            (r * mt.Tensor(np.arange(r.size, dtype=np.float32).reshape(r.shape) / r.size, device=dev)).sum().backward()
+            outs.append((host(r.data), host(x.grad), host(y.grad)))
+        for a, b in zip(*outs):
+            np.testing.assert_array_equal(a, b)
+
+    for op in ("__lt__", "__gt__", "__le__", "__ge__", "__eq__", "__ne__"):
+        c = getattr(mt.Tensor(xv, device="cuda"), op)(mt.Tensor(yv, device="cuda"))
+        assert c.device.value == "cuda"                                          # masks stay on the device
+        np.testing.assert_array_equal(host(c.data), getattr(xv, op)(yv).astype(np.float32))
+    both(lambda x, y: mt.Tensor.where(x > y, x, y))
+    both(lambda x, y: mt.Tensor.maximum(x, y) + mt.Tensor.minimum(x, y * 2))
+    both(lambda x, y: x.abs() + y.abs())
+    both(lambda x, y: x.threshold(0.25, -1.0) + y.clip(-0.5, 0.5))
+    both(lambda x, y: x.masked_fill(y > 0, 3.0) + y.sign() * x)
+    for dev in ("cpu", "cuda"):
+        p = mt.Tensor(xv, requires_grad=True, device=dev)
+        l = L1Loss()(p, mt.Tensor(yv, device=dev))
+        l.backward()
+        if dev == "cpu":
+            ref = (l.data.copy(), p.grad.copy())
+        else:
+            np.testing.assert_allclose(host(l.data), ref[0], rtol=1e-6)
+            np.testing.assert_array_equal(host(p.grad), ref[1])
+    for dev in ("cpu", "cuda"):
+        t = mt.Tensor(xv, requires_grad=True, device=dev)
+        (t * 3.0).sum().backward()
+        t.grad = t.grad * mt.Tensor(yv, device=dev).data
+        t.clip_grad(0.5)
+        g1 = host(t.grad)
+        t.clip_grad_norm(max_norm=1.0)
+        g2 = host(t.grad)
+        if dev == "cpu":
+            refs = (g1, g2)
+        else:
+            np.testing.assert_array_equal(g1, refs[0])
+            np.testing.assert_allclose(g2, refs[1], rtol=1e-5)
+
+
+def test_exp_sqrt_detach_clone_on_cuda(mt):
+    """Section 8(f) item 2: the cheap math / utility ops on the device."""
+    rng = np.random.default_rng(22)
+    xv = rng.uniform(0.5, 2.0, (17, 9)).astype(np.float32)
+    x = mt.Tensor(xv, requires_grad=True, device="cuda")
+    r = x.exp() + x.sqrt()
+    r.sum().backward()
+    np.testing.assert_allclose(host(r.data), np.exp(xv) + np.sqrt(xv), rtol=1e-6)
+    np.testing.assert_allclose(host(x.grad), np.exp(xv) + 0.5 / np.sqrt(xv), rtol=1e-5)
+    d = x.detach()
+    assert not d.requires_grad and d.device.value == "cuda"
+    c = x.clone()
+    np.testing.assert_array_equal(host(c.data), xv)
+    assert c.data.ptr != x.data.ptr

@@ -480,3 +480,83 @@ def test_exp_sqrt_detach_clone_on_cuda(mt):
     c = x.clone()
     np.testing.assert_array_equal(host(c.data), xv)
     assert c.data.ptr != x.data.ptr
+
+
+def test_c2_full_width_16384_rows_one_step_vs_oracle(mt):
+    """BASELINE config #2 at FULL layer widths (1024->4096->4096->10) and a quarter of the batch (16384 rows, ~3 s
+    on the CPU oracle): loss, every weight gradient and post-SGD weight against the oracle, 1e-4 norm-wise.
+    Exercises the CTA-pair GEMMs with split-K dW, the chain-fused tanh' epilogues and the skinny head."""
+    from oracle import workloads as OW
+    wl = W.scaled(W.C2, 16384)
+    ref = OW.run_steps(wl, 1)
+    res = run_cuda(mt, wl, 1)
+    np.testing.assert_allclose(res["losses"], ref["losses"], rtol=1e-4)
+    for i, (gr, pr) in enumerate(zip(res["grads"], res["params"])):
+        gemm_close(pr, ref["params"][i])
+        gemm_close(gr, ref["grads"][i])
+        if i % 2:
+            assert not gr.any()
+
+
+def test_c4_full_size_forward_vs_oracle(mt):
+    """BASELINE config #4 at full size - one forward of the 3-D Linear stack (256 x 512 x 2048, two layers) - against
+    the oracle ('parity at reduced (8,64,256) and one full-size forward')."""
+    from oracle import workloads as OW
+    wl = W.Workload("c4_full", (2048, 2048, 2048), "bce", 0.01, 256, pred_map=(0.49, 0.5), seed=0,
+                    input_shape=(256, 512, 2048))
+    omodel, ox, _ = OW.setup(wl)
+    want = OW.forward_only(wl, omodel, ox)
+    model, x, _ = W.setup(wl, mt.Linear, mt.Tanh, mt.Sequential)
+    got = model(mt.Tensor(x, device="cuda"))
+    assert got.shape == (256, 512, 2048)
+    gemm_close(got.data, want)
+
+
+def test_prefetch_pipeline_delivers_exact_bytes(mt):
+    """Pinned staging + copy-stream prefetch (the e2e input pipeline of bench.py): double-buffered uploads arrive intact
+    while the compute stream is busy."""
+    from microtorch_b200 import cuda as mtcuda
+    rng = np.random.default_rng(30)
+    stage = mtcuda.pinned_empty((1 << 20,))
+    busy = mt.Tensor(rng.standard_normal((2048, 2048)).astype(np.float32), device="cuda")
+    pending = None
+    for i in range(6):
+        batch = rng.standard_normal(1 << 20).astype(np.float32)
+        if pending is not None:
+            mtcuda.wait_prefetch()
+            np.testing.assert_array_equal(host(pending[0]), pending[1])
+        mt.lib.mt_sync()                       # the staging buffer is reused: the previous copy must be done
+        stage[...] = batch
+        pending = (mtcuda.prefetch(stage), batch)
+        busy = (busy @ busy) * 1e-3            # compute overlapping the copy
+    mtcuda.wait_prefetch()
+    np.testing.assert_array_equal(host(pending[0]), pending[1])
+
+
+def test_empty_and_ragged_inputs(mt):
+    """Edge cases: empty batches, extent-1 axes, odd sizes, 0-d tensors."""
+    e = mt.Tensor(np.zeros((0, 7), np.float32), requires_grad=True, device="cuda")
+    r = (e * 2.0 + 1.0).tanh()
+    assert r.shape == (0, 7) and host(r.data).shape == (0, 7)
+    s = r.sum()
+    assert s.item() == 0.0
+    s.backward()
+    assert host(e.grad).shape == (0, 7)
+    np.random.seed(2)
+    lin = mt.Linear(7, 5)
+    out = lin(mt.Tensor(np.zeros((0, 7), np.float32), device="cuda"))
+    assert out.shape == (0, 5)
+    rng = np.random.default_rng(31)
+    for shape_x, shape_y in [((1, 1), (1,)), ((13, 1, 7), (5, 1)), ((3,), ()), ((2, 3, 5, 7), (3, 1, 7))]:
+        xv = rng.uniform(0.5, 1.5, shape_x).astype(np.float32)
+        yv = rng.uniform(0.5, 1.5, shape_y).astype(np.float32)
+        outs = []
+        for dev in ("cpu", "cuda"):
+            x = mt.Tensor(xv, requires_grad=True, device=dev)
+            y = mt.Tensor(yv, requires_grad=True, device=dev)
+            z = (x * y + x ** 2 - y).log().tanh()
+            z.sum().backward()
+            outs.append((host(z.data), host(x.grad), host(y.grad)))
+        for a, b in zip(*outs):
+            assert a.shape == b.shape
+            np.testing.assert_allclose(b, a, rtol=1e-5, atol=1e-6)

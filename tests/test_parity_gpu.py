@@ -560,3 +560,54 @@ def test_empty_and_ragged_inputs(mt):
         for a, b in zip(*outs):
             assert a.shape == b.shape
             np.testing.assert_allclose(b, a, rtol=1e-5, atol=1e-6)
+
+
+def test_bare_matmul_views_on_tensor_cores(mt):
+    """The generic `@` (overload.py:130-164) with transposed / strided operand views at sizes the tcgen05 engine takes:
+    all four operand-major combinations, a row-sliced operand (pitch > extent), forward and both gradients."""
+    import ctypes as C
+    rng = np.random.default_rng(40)
+    M, K, N = 512, 384, 256
+    for ta in (False, True):
+        for tb in (False, True):
+            av = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+            bv = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+            a = mt.Tensor(av, requires_grad=True, device="cuda")
+            b = mt.Tensor(bv, requires_grad=True, device="cuda")
+            c = (a.T if ta else a) @ (b.T if tb else b)
+            eng = C.c_int(-9)
+            mt.lib.mt_gemm_last_engine(C.byref(eng))
+            assert eng.value == 1, (ta, tb)                      # ran on tcgen05, no transposed copies
+            gw = rng.standard_normal((M, N)).astype(np.float32)
+            (c * mt.Tensor(gw, device="cuda")).sum().backward()
+            A64 = (av.T if ta else av).astype(np.float64)
+            B64 = (bv.T if tb else bv).astype(np.float64)
+            gemm_close(c.data, A64 @ B64, 1e-5)
+            ga, gb = gw.astype(np.float64) @ B64.T, A64.T @ gw.astype(np.float64)
+            gemm_close(a.grad, ga.T if ta else ga, 1e-5)
+            gemm_close(b.grad, gb.T if tb else gb, 1e-5)
+    big = mt.Tensor(rng.standard_normal((600, 512)).astype(np.float32), device="cuda")
+    sl = big[40:552, 64:448]                                      # 512 x 384 view, pitch 512 > 384
+    w = mt.Tensor(rng.standard_normal((384, 256)).astype(np.float32), device="cuda")
+    gemm_close((sl @ w).data, host(big.data)[40:552, 64:448].astype(np.float64) @ host(w.data), 1e-5)
+
+
+def test_inplace_ops_on_cuda(mt):
+    """Tensor.__iadd__/__isub__/__imul__/__itruediv__ (tensor.py:547-616) incl. a strided destination."""
+    rng = np.random.default_rng(41)
+    xv = rng.standard_normal((12, 20)).astype(np.float32)
+    bv = rng.uniform(0.5, 1.5, (1, 20)).astype(np.float32)
+    want = xv.copy()
+    x = mt.Tensor(xv, device="cuda")
+    b = mt.Tensor(bv, device="cuda")
+    x += b; want += bv
+    x -= 0.25; want -= np.float32(0.25)
+    x *= b; want *= bv
+    x /= 2.0; want /= np.float32(2.0)
+    np.testing.assert_array_equal(host(x.data), want)
+    base = mt.Tensor(xv, device="cuda")
+    view = base.T                                                  # F-contiguous view, as Linear's output in the reference
+    view += mt.Tensor(rng.standard_normal((20, 1)).astype(np.float32), device="cuda")
+    assert host(base.data).shape == (12, 20)
+    col = host(view.data) - xv.T
+    assert np.allclose(col, col[:, :1])                            # one value per row of the view was added

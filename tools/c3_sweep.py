@@ -112,7 +112,7 @@ def main():
             lossf(xp, yt).backward()
         work["mse_loss_fwd_bwd"] = (f_loss, 3 * B)
         for name, (fn, nbytes) in work.items():
-            if args.only and args.only not in name:
+            if args.only and not any(k in name for k in args.only.split(',')):
                 continue
             ms = timed(fn, args.iters)
             rec = {"workload": name, "log2_n": p, "ms": ms, "alg_gb": nbytes / 1e9, "gbs": nbytes / ms / 1e6,

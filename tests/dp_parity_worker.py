@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Data-parallel parity on real GPUs (launched by torchrun, one rank per GPU): N-rank post-SGD weights and
+"""Worker of tests/test_dp_gpu.py (lives under tests/ because it checks against the oracle).
+Data-parallel parity on real GPUs (launched by torchrun, one rank per GPU): N-rank post-SGD weights and
 global loss against the oracle (CPU) on a small global batch; 1e-4 norm-wise.  Rank 0 prints one JSON line."""
 import json
 import os

@@ -16,7 +16,7 @@ def test_two_gpu_dp_matches_oracle():
     if _capi.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(REPO, "tools", "dp_parity.py")],
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(REPO, "tests", "dp_parity_worker.py")],
                        capture_output=True, text=True, timeout=600)
     line = [l for l in r.stdout.splitlines() if l.startswith("DP_PARITY ")]
     assert line, r.stdout[-2000:] + r.stderr[-2000:]

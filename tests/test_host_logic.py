@@ -64,6 +64,19 @@ def test_product_never_imports_the_oracle_or_torch():
     assert not bad, bad
 
 
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """tools/ and the package must not import the oracle (it is the checker, never the thing measured or shipped)."""
+    bad = []
+    for sub in ("tools", "microtorch_b200"):
+        for root, _, files in os.walk(os.path.join(REPO, sub)):
+            for f in files:
+                if f.endswith(".py"):
+                    path = os.path.join(root, f)
+                    if any(m.lstrip(".").split(".")[0] == "oracle" for m in _imports(path)):
+                        bad.append(path)
+    assert not bad, bad
+
+
 def test_cuda_requested_without_backend_raises():
     from microtorch_b200 import _capi
     from microtorch_b200.tensor import Tensor

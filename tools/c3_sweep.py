@@ -7,7 +7,7 @@ Workloads, x,y ~ U(0.5,1.5) fp32, N in 2^20..2^28 (2^30 with --bi
   log    x.log().sum().backward()      tanh   x.tanh().sum().backward()
   sum    x.sum()      mean   x.mean() + backward      sum0/sum1  x.sum(axis=0/1)
 Bytes are ALGORITHMIC: the sum of the per-kernel minimum traffic of the launches
-the workload needs.  One JSON line per (workload, N); --cpu adds the oracle's time for N <= 2^24."""
+the workload needs.  One JSON line per (workload, N)."""
 import argparse
 import ctypes as C
 import json
@@ -25,7 +25,6 @@ def main():
     ap.add_argument("--max", type=int, default=28)
     ap.add_argument("--step", type=int, default=2)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--only", default="")
     args = ap.parse_args()
     from microtorch_b200 import _capi

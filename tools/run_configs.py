@@ -5,7 +5,8 @@
   c4          3-D Linear stack (256 x 512 x 2048, k layers) + BCELoss: samples/s, GEMM TFLOP/s
   c5          4096-wide x 8 layers, 65536 rows per GPU (the per-GPU share of global batch 524288 at 8 GPUs)
 
-One JSON line per config; `--cpu` adds the oracle (CPU port of the reference) on a bounded sample."""
+One JSON line per config.  (The CPU-port timings of the same configs come from tests/cpu_config_baselines.py:
+only tests/, smoke() and bench.py's CPU legs may touch the oracle.)"""
 import argparse
 import ctypes as C
 import json
@@ -20,7 +21,6 @@ import numpy as np  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
-    ap.add_argument("--cpu", action="store_true")
     ap.add_argument("--c4-layers", type=int, default=2)
     args = ap.parse_args()
     from microtorch_b200 import _capi, workloads as W
@@ -73,18 +73,6 @@ def main():
         del model, X, T
         lib.mt_pool_trim()
 
-    def cpu(wl, steps, tag):
-        from oracle import workloads as OW
-        from oracle.nnref import train_step as ostep
-        model, x, t = OW.setup(wl)
-        ostep(model, x, t, wl.loss, wl.lr, wl.pred_map, wl.squeeze_dim, x.ndim == 3)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            ostep(model, x, t, wl.loss, wl.lr, wl.pred_map, wl.squeeze_dim, x.ndim == 3)
-        dt = (time.perf_counter() - t0) / steps
-        print(json.dumps({"config": tag + "_cpu_oracle", "ms_per_step": dt * 1e3, "samples_per_s": wl.batch / dt,
-                          "host_cpus": os.cpu_count()}), flush=True)
-
     def run_graphed(wl, steps, tag):
         from microtorch_b200.graph import GraphedStep
         model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
@@ -110,25 +98,16 @@ def main():
     if want("c1a"):
         run(W.C1A, 2000, 50, "c1a_spiral_notebook_mlp_2_64_32_16_1")
         run_graphed(W.C1A, 5000, "c1a_spiral_notebook_mlp_2_64_32_16_1")
-        if args.cpu:
-            cpu(W.C1A, 500, "c1a")
     if want("c1b"):
         run(W.C1B, 2000, 50, "c1b_spiral_2_100_3")
         run_graphed(W.C1B, 5000, "c1b_spiral_2_100_3")
-        if args.cpu:
-            cpu(W.C1B, 500, "c1b")
     if want("c4"):
         k = args.c4_layers
         wl = W.Workload("c4", (2048,) * (k + 1), "bce", 0.01, 256, pred_map=(0.49, 0.5), seed=0, input_shape=(256, 512, 2048))
         run(wl, 5, 2, f"c4_3d_linear_256x512x2048_k{k}_bce", {"gemm_flops_per_step": wl.gemm_flops_per_step()})
-        if args.cpu:
-            cpu(W.Workload("c4s", (2048,) * (k + 1), "bce", 0.01, 8, pred_map=(0.49, 0.5), seed=0, input_shape=(8, 512, 2048)),
-                1, "c4_at_8x512x2048")
     if want("c5"):
         wl = W.scaled(W.C5, 65536)
         run(wl, 4, 2, "c5_mlp_4096x8_rows65536_per_gpu", {"gemm_flops_per_step": wl.gemm_flops_per_step()})
-        if args.cpu:
-            cpu(W.scaled(W.C5, 2048), 1, "c5_at_2048_rows")
 
 
 if __name__ == "__main__":

@@ -180,6 +180,11 @@ int mt_ew_where_f32(float* out, const float* cond, const float* a, const float* 
 int mt_reduce_sum_f32(float* out, const float* x, int64_t outer, int64_t red, int64_t inner,
                       const float* other, int64_t other_so, int64_t other_sr, int64_t other_si);
 
+/* out[o,i] = max_r (is_max != 0) or min_r x[o,r,i], x contiguous [outer, red, inner], red > 0.  NaN propagates.
+ * replaces: tlib.max / tlib.min(x, axis, keepdims) in Reduce.max / Reduce.min (reduce.py:66,87); their backward
+ * (reduce.py:46-63) is composed from MT_BIN_EQ, mt_reduce_sum_f32, MT_BIN_DIV and MT_BIN_MUL.            */
+int mt_reduce_extreme_f32(int is_max, float* out, const float* x, int64_t outer, int64_t red, int64_t inner);
+
 /* ---------------------------------------------------------------- Linear / matmul -- */
 typedef enum mt_act { MT_ACT_NONE = 0, MT_ACT_TANH = 1 } mt_act;
 

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "mt_ew_unary_f32": [C.c_int, VP, VP, C.c_size_t, C.c_float],
     "mt_ew_where_f32": [VP, VP, VP, VP, C.c_int, c_i64p, c_i64p, c_i64p, c_i64p],
     "mt_reduce_sum_f32": [VP, VP, C.c_int64, C.c_int64, C.c_int64, VP, C.c_int64, C.c_int64, C.c_int64],
+    "mt_reduce_extreme_f32": [C.c_int, VP, VP, C.c_int64, C.c_int64, C.c_int64],
     "mt_linear_fwd_f32": [VP, VP, VP, VP, C.c_int64, C.c_int64, C.c_int64, C.c_int],
     "mt_linear_bwd_f32": [VP, VP, VP, VP, VP, VP, C.c_int64, C.c_int64, C.c_int64, C.c_int],
     "mt_matmul_f32": [VP, VP, VP] + [C.c_int64] * 10,

@@ -320,8 +320,10 @@ int launch_binary(float* out, const float* a, const float* b, int ndim, const in
     MT_LAUNCHED();
     return MT_OK;
   }
-  if (n == 2 && al && (ca[1] == 0 || ca[1] == 1) && (cb[1] == 0 || cb[1] == 1) && cs[1] % 4 == 0 && ca[0] % 4 == 0 &&
-      cb[0] % 4 == 0 && ca[0] >= 0 && cb[0] >= 0) {
+  // row pitch must keep float4 loads aligned only for an operand that is read along the row (inner stride 1);
+  // a column operand (inner stride 0: one scalar per row, e.g. shape (R,1)) may have any pitch
+  if (n == 2 && al && (ca[1] == 0 || ca[1] == 1) && (cb[1] == 0 || cb[1] == 1) && cs[1] % 4 == 0 &&
+      (ca[1] == 0 || ca[0] % 4 == 0) && (cb[1] == 0 || cb[0] % 4 == 0) && ca[0] >= 0 && cb[0] >= 0) {
     const long long R = cs[0], C4 = cs[1] / 4;
     const int grid = ew_grid(R * C4, THREADS * UNROLL);
     const int key = (ca[1] ? 2 : 0) | (cb[1] ? 1 : 0);

@@ -240,7 +240,123 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
   return MT_OK;
 }
 
+// ------------------------------------------------------------ max / min (Reduce.max / Reduce.min forward)
+// Selection, so the result is bit-exact and order-independent; NaN wins like np.max / np.min.
+template <bool IS_MAX>
+__device__ __forceinline__ float pick(float a, float b) {
+  return ((IS_MAX ? a > b : a < b) || a != a) ? a : b;
+}
+
+template <bool IS_MAX>
+__device__ __forceinline__ float block_pick(float v, float* smem) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = pick<IS_MAX>(v, __shfl_xor_sync(0xffffffffu, v, d));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  v = smem[0];
+#pragma unroll
+  for (int w = 1; w < THREADS / 32; ++w) v = pick<IS_MAX>(v, smem[w]);
+  return v;
+}
+
+// inner == 1: item = (row, split); every thread starts from the first element of its item's range
+template <bool IS_MAX>
+__global__ void __launch_bounds__(THREADS) extreme_rows_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                               long long outer, long long red, long long splits,
+                                                               long long chunk) {
+  __shared__ float smem[THREADS / 32];
+  const long long items = outer * splits;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long o = item / splits, s = item - o * splits;
+    const long long r0 = s * chunk;
+    long long r1 = r0 + chunk;
+    if (r1 > red) r1 = red;
+    const float* px = x + o * red;
+    float acc = px[r0];
+    const bool vec = ((reinterpret_cast<uintptr_t>(px + r0) & 15) == 0);
+    long long j = r0;
+    if (vec) {
+      const long long nv = (r1 - r0) >> 2;
+      for (long long i = threadIdx.x; i < nv; i += THREADS) {
+        const float4 a = mtd::ld_stream4(px + r0 + 4 * i);
+        acc = pick<IS_MAX>(acc, pick<IS_MAX>(pick<IS_MAX>(a.x, a.y), pick<IS_MAX>(a.z, a.w)));
+      }
+      j = r0 + (nv << 2);
+    }
+    for (long long k = j + threadIdx.x; k < r1; k += THREADS) acc = pick<IS_MAX>(acc, px[k]);
+    const float t = block_pick<IS_MAX>(acc, smem);
+    if (threadIdx.x == 0) out[item] = t;
+  }
+}
+
+// inner > 1: one thread per (outer, split, column), coalesced across columns
+template <bool IS_MAX>
+__global__ void __launch_bounds__(THREADS) extreme_cols_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                               long long outer, long long red, long long inner,
+                                                               long long splits, long long chunk) {
+  const long long total = outer * splits * inner;
+  const long long stride = (long long)gridDim.x * THREADS;
+  for (long long t = (long long)blockIdx.x * THREADS + threadIdx.x; t < total; t += stride) {
+    const long long col = t % inner, os = t / inner;
+    const long long s = os % splits, o = os / splits;
+    const long long r0 = s * chunk;
+    long long r1 = r0 + chunk;
+    if (r1 > red) r1 = red;
+    const float* px = x + (o * red) * inner + col;
+    float acc = px[r0 * inner];
+    for (long long r = r0 + 1; r < r1; ++r) acc = pick<IS_MAX>(acc, __ldg(px + r * inner));
+    out[t] = acc;
+  }
+}
+
+template <bool IS_MAX>
+int reduce_extreme(float* out, const float* x, long long outer, long long red, long long inner) {
+  cudaStream_t st = g().stream;
+  const long long sms = g().sm_count;
+  long long splits = 1;
+  if (inner == 1) {
+    if (outer < 2 * sms) splits = std::max<long long>(1, std::min<long long>(ceil_div(4 * sms, outer), ceil_div(red, 4096)));
+  } else if (outer * inner < 64 * sms * THREADS / 32) {
+    splits = std::max<long long>(1, std::min<long long>(ceil_div(64 * sms * THREADS / 32, outer * inner), ceil_div(red, 64)));
+  }
+  long long chunk = ceil_div(red, splits);
+  chunk = (chunk + 3) & ~3LL;
+  splits = ceil_div(red, chunk);
+  float* dst = out;
+  float* partial = nullptr;
+  if (splits > 1) {
+    int rc = pool_alloc((void**)&partial, sizeof(float) * outer * splits * inner);
+    if (rc) return rc;
+    dst = partial;
+  }
+  if (inner == 1) {
+    const int grid = (int)std::min<long long>(outer * splits, sms * 8);
+    extreme_rows_kernel<IS_MAX><<<grid, THREADS, 0, st>>>(dst, x, outer, red, splits, chunk);
+  } else {
+    const int grid = (int)std::min<long long>(ceil_div(outer * splits * inner, THREADS), sms * 16);
+    extreme_cols_kernel<IS_MAX><<<grid, THREADS, 0, st>>>(dst, x, outer, red, inner, splits, chunk);
+  }
+  MT_LAUNCHED();
+  if (splits > 1) {
+    int rc = reduce_extreme<IS_MAX>(out, partial, outer, splits, inner);
+    pool_free(partial);  // stream-ordered
+    return rc;
+  }
+  return MT_OK;
+}
+
 }  // namespace
+
+MT_API int mt_reduce_extreme_f32(int is_max, float* out, const float* x, int64_t outer, int64_t red, int64_t inner) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(out && x, "mt_reduce_extreme_f32: null pointer");
+  MT_CHECK_ARG(outer >= 0 && red >= 0 && inner >= 0, "mt_reduce_extreme_f32: negative extent");
+  if (outer * inner == 0) return MT_OK;
+  MT_CHECK_ARG(red > 0, "mt_reduce_extreme_f32: zero-size array to reduction operation which has no identity");
+  return is_max ? reduce_extreme<true>(out, x, outer, red, inner) : reduce_extreme<false>(out, x, outer, red, inner);
+}
 
 MT_API int mt_reduce_sum_f32(float* out, const float* x, int64_t outer, int64_t red, int64_t inner, const float* other,
                              int64_t so, int64_t sr, int64_t si) {

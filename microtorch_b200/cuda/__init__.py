@@ -2,8 +2,8 @@
 
 It stands where the `cupy` module stands in the reference (src/tensor/device.py:74-84):
 the NumPy-API names the reference calls on the module object, all
-backed by libmicrotorch_b200.so.  Names that the training path never calls on CUDA and
-are not implemented (max / min reductions) raise; comparisons, where, clip, abs and norm run on the device.
+backed by libmicrotorch_b200.so (reductions incl. max / min, comparisons, where, clip, abs and norm run
+on the device).
 """
 
 from __future__ import annotations
@@ -202,5 +202,9 @@ class linalg:                      # noqa: N801  (NumPy name)
         return float(kernels.reduce_sum(powed, axes).item()) ** (1.0 / p)
 
 
-max = _unsupported("max")          # noqa: A001
-min = _unsupported("min")          # noqa: A001
+def max(x, axis=None, keepdims=False):          # noqa: A001 (NumPy name)
+    return kernels.extreme(x, axis, keepdims, True)
+
+
+def min(x, axis=None, keepdims=False):          # noqa: A001 (NumPy name)
+    return kernels.extreme(x, axis, keepdims, False)

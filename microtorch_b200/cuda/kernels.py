@@ -212,6 +212,31 @@ def sum(x: DeviceArray, axis=None, keepdims: bool = False) -> DeviceArray:      
     return res
 
 
+def extreme(x: DeviceArray, axis=None, keepdims: bool = False, is_max: bool = True) -> DeviceArray:
+    """np.max / np.min(x, axis, keepdims) (Reduce.max / Reduce.min forward, reference reduce.py:66,87)."""
+    x = _as_device(x)
+    nd = x.ndim
+    if axis is None:
+        axes = tuple(range(nd))
+    elif isinstance(axis, (tuple, list)):
+        axes = tuple(int(a) % nd for a in axis)
+    else:
+        axes = (int(axis) % nd,)
+    if x.size == 0:
+        raise ValueError("zero-size array to reduction operation which has no identity")
+    kept = [d for i, d in enumerate(x.shape) if i not in axes]
+    cur = x.dense()
+    for outer, red, inner in plan_reduction(x.shape, axes):
+        out = DeviceArray.empty((outer * inner,))
+        _capi.check(_lib().mt_reduce_extreme_f32(1 if is_max else 0, out.ptr, cur.ptr, outer, red, inner),
+                    "mt_reduce_extreme_f32")
+        cur = out
+    res = cur.reshape(kept) if cur is not x else cur.copy().reshape(kept)
+    if keepdims:
+        return res.reshape([1 if i in axes else d for i, d in enumerate(x.shape)])
+    return res
+
+
 def unbroadcast(grad: DeviceArray, shape: Sequence[int], other: Optional[DeviceArray] = None) -> DeviceArray:
     """BaseOps.bkwd_broadcast (reference base.py:8-58) with an optional fused `grad * other`
     (mul backward, overload.py:109-112): fold `grad` onto an operand of `shape`."""

@@ -50,6 +50,12 @@ class CpuBackend:
     def matmul(a, b): return a @ b
     @staticmethod
     def sum(x, axis, keepdims): return np.sum(x, axis=axis, keepdims=keepdims)
+    @staticmethod
+    def extreme(x, axis, keepdims, is_max): return (np.max if is_max else np.min)(x, axis=axis, keepdims=keepdims)
+    @staticmethod
+    def equal(a, b): return a == b
+    @staticmethod
+    def div(a, b): return a / b
 
     # -- backward -----------------------------------------------------------------------
     @staticmethod
@@ -147,6 +153,9 @@ class CudaBackend:
     def pow(self, x, p): return self.K.unary(_capi.UN_POW, x, float(p))
     def matmul(self, a, b): return self.K.matmul(a, b)
     def sum(self, x, axis, keepdims): return self.K.sum(x, axis, keepdims)
+    def extreme(self, x, axis, keepdims, is_max): return self.K.extreme(x, axis, keepdims, is_max)
+    def equal(self, a, b): return self.K.binary(_capi.BIN_EQ, a, b)
+    def div(self, a, b): return self.K.binary(_capi.BIN_DIV, a, b)
 
     # -- backward (fused) ---------------------------------------------------------------
     def unbroadcast(self, grad, shape, other=None): return self.K.unbroadcast(grad, shape, other)

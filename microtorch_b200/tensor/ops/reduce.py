@@ -4,9 +4,6 @@ from __future__ import annotations
 
 from typing import Optional
 
-import numpy as np
-
-from ..device import Device
 from ..types import Axis, TensorLike, TProps
 from ._tape import be, record
 
@@ -27,28 +24,27 @@ class Reduce:
 
     @staticmethod
     def bkwd_minmax(tensor: TensorLike, output, axis: Optional[Axis], keepdims: bool = False):
-        if tensor.device != Device.CPU:
-            raise NotImplementedError("max/min are not part of the CUDA training path (SURVEY.md section 8f)")
+        """The gradient is shared equally between the tied extreme elements (reference reduce.py:46-63).
+        CUDA: compare, count, divide and mask are four launches of the existing kernels."""
+        backend, x = be(tensor), tensor.data
 
         def share(grad):
-            hit = (tensor.data == output)
-            n = np.sum(hit) if axis is None else np.sum(hit, axis=axis, keepdims=True)
-            g = grad if (keepdims or axis is None) else np.expand_dims(grad, axis=axis)
-            return hit * (g / n)
+            hit = backend.equal(x, output)
+            n = backend.sum(hit, None if axis is None else axis, axis is not None)
+            g = grad if (keepdims or axis is None) else backend.expand_dims(grad, axis)
+            return backend.mul(hit, backend.div(g, n))
 
         return share
 
     @staticmethod
-    def _extreme(fn, tensor: TensorLike, axis, keepdims) -> TProps:
-        if tensor.device != Device.CPU:
-            raise NotImplementedError("max/min are not part of the CUDA training path (SURVEY.md section 8f)")
-        out = fn(tensor.data, axis=axis, keepdims=keepdims)
+    def _extreme(is_max: bool, tensor: TensorLike, axis, keepdims) -> TProps:
+        out = be(tensor).extreme(tensor.data, axis, keepdims, is_max)
         return record(out, tensor, [(tensor, Reduce.bkwd_minmax(tensor, out, axis, keepdims))])
 
     @staticmethod
     def max(tensor: TensorLike, axis: Optional[Axis], keepdims: bool = False) -> TProps:
-        return Reduce._extreme(np.max, tensor, axis, keepdims)
+        return Reduce._extreme(True, tensor, axis, keepdims)
 
     @staticmethod
     def min(tensor: TensorLike, axis: Optional[Axis], keepdims: bool = False) -> TProps:
-        return Reduce._extreme(np.min, tensor, axis, keepdims)
+        return Reduce._extreme(False, tensor, axis, keepdims)

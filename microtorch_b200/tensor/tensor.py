@@ -263,9 +263,13 @@ class Tensor(TensorLike):
         if cur is None or cur is _LAZY:
             # adopt; an array already adopted elsewhere is copied so two tensors never share a
             # buffer that zero_grad()/SGD may later write in place
-            if g._owned or g._const:
-                g = g.copy()
-            g._owned = True
+            # A broadcast / strided view (sum().backward()'s stride-0 gradient travelling down a chain of
+            # adds) is adopted as is, however many tensors hold it: nothing writes through a view, and
+            # the `grad` getter makes a private dense array of it on first read.
+            if g.is_dense:
+                if g._owned or g._const:
+                    g = g.copy()
+                g._owned = True
             self._grad = g
         else:
             acc = backend_for(self._device).accumulate(cur, g)

@@ -132,6 +132,7 @@ class DataParallelTrainer:
         self.optimizer = SGD(model.parameters, lr=lr)
         self.pred_map, self.squeeze_dim = pred_map, squeeze_dim
         self.exchanged_bytes = 0
+        self.steps = 0
 
     def _on_grad_final(self, param: Tensor) -> None:
         g = param._grad
@@ -164,7 +165,22 @@ class DataParallelTrainer:
         if self.comm is not None and self.world > 1:
             self.comm.wait()
         self.optimizer.step()
+        self.steps += 1
         return loss
+
+    # -- resume: every rank holds the same replica, so rank 0 writes, all ranks read
+    def save_checkpoint(self, path) -> None:
+        from .checkpoint import save_checkpoint
+        if self.comm is None or self.comm.rank == 0:
+            save_checkpoint(path, self.model, step=self.steps, lr=self.optimizer.lr, extra={"world": self.world})
+
+    def load_checkpoint(self, path) -> dict:
+        from .checkpoint import load_checkpoint
+        header = load_checkpoint(path, self.model)
+        self.steps = int(header.get("step", 0))
+        if header.get("lr") is not None:
+            self.optimizer.lr = float(header["lr"])
+        return header
 
     def global_loss(self, local_loss: Tensor) -> float:
         """Sum of the rank partial losses (host value; synchronises)."""

@@ -33,7 +33,7 @@ def binary(lib, op, a, b, scalar=0.0):
 
 SHAPES = [((6, 8), (6, 8)), ((64, 4096), (1, 4096)), ((64, 4096), (64, 1)), ((37, 129), ()), ((3, 6, 8), (8,)),
           ((3, 6, 8), (1, 6, 1)), ((1 << 20,), (1 << 20,)), ((1000003,), (1000003,)), ((5, 1, 7), (1, 4, 1)),
-          ((0, 4), (1, 4))]
+          ((0, 4), (1, 4)), ((129, 260), (129, 1)), ((1, 260), (129, 1))]
 
 
 @pytest.mark.parametrize("sa,sb", SHAPES)
@@ -98,6 +98,24 @@ def test_reduce_sum(lib, outer, red, inner):
     want = x.astype(np.float64).sum(axis=1)
     np.testing.assert_allclose(got, want, rtol=1e-5)
     np.testing.assert_allclose(got, x.sum(axis=1), rtol=1e-5)          # and against NumPy's fp32 pairwise sum
+
+
+@pytest.mark.parametrize("outer,red,inner", [(1, 1 << 22, 1), (1, 1000003, 1), (1024, 4096, 1), (5000, 10, 1), (7, 33, 1),
+                                             (1, 8192, 4096), (1, 131, 2048), (3, 1000, 36), (256, 3, 2), (1, 1, 5),
+                                             (1, 70000, 12), (2, 5, 3)])
+def test_reduce_extreme_bit_exact(lib, outer, red, inner):
+    """Reduce.max / Reduce.min forward: selection, so bit-exact against np.max / np.min, NaN included."""
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal((outer, red, inner)).astype(np.float32)
+    dx, out = Dev(x), Dev(shape=(outer, inner))
+    for is_max, fn in ((1, np.max), (0, np.min)):
+        _capi.check(lib.mt_reduce_extreme_f32(is_max, out.ptr, dx.ptr, outer, red, inner))
+        np.testing.assert_array_equal(out.get(), fn(x, axis=1))
+    x[0, red // 2, 0] = np.nan                                          # NaN propagates like NumPy's max / min
+    dx = Dev(x)
+    for is_max, fn in ((1, np.max), (0, np.min)):
+        _capi.check(lib.mt_reduce_extreme_f32(is_max, out.ptr, dx.ptr, outer, red, inner))
+        np.testing.assert_array_equal(out.get(), fn(x, axis=1))
 
 
 def test_reduce_sum_fused_multiply(lib):

@@ -111,3 +111,50 @@ def test_cpu_path_training_step_matches_oracle():
         np.testing.assert_allclose(losses, ref["losses"], rtol=1e-5)
         for p, want in zip(model.parameters(), ref["params"]):
             np.testing.assert_allclose(p.data, want, rtol=1e-5, atol=1e-7)
+
+
+def test_checkpoint_round_trip_and_resume_cpu(tmp_path):
+    """a model checkpoint resumes the trajectory bit-exactly (Device.CPU), loads in
+    place (the optimizer keeps working on the same Parameter objects) and rejects mismatching files."""
+    from microtorch_b200 import checkpoint as ck, workloads as W
+    import microtorch_b200.nn as nn
+    from microtorch_b200.nn.activation import Tanh
+    from microtorch_b200.nn.loss import MSELoss
+    from microtorch_b200.nn.optimizer import SGD
+    from microtorch_b200.tensor import Tensor
+    from microtorch_b200.trainer import train_step
+    wl = W.C1A
+    model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+    X, T, opt, loss_fn = Tensor(x), Tensor(t), SGD(model.parameters, lr=wl.lr), MSELoss()
+    for _ in range(3):
+        train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim)
+    names = [n for n, _ in ck.named_parameters(model)]
+    assert names[:2] == ["modules.0.weight", "modules.0.bias"] and len(names) == len(list(model.parameters()))
+    path = tmp_path / "c1a.npz"
+    ck.save_checkpoint(path, model, step=3, lr=wl.lr, extra={"note": "x"})
+    want = [train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim).item() for _ in range(3)]
+    final = [np.array(p.data, copy=True) for p in model.parameters()]
+
+    fresh, _, _ = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+    held = list(fresh.parameters())
+    header = ck.load_checkpoint(path, fresh)
+    assert header["step"] == 3 and header["lr"] == wl.lr and header["extra"] == {"note": "x"}
+    assert [id(p) for p in fresh.parameters()] == [id(p) for p in held]          # loaded in place
+    opt2 = SGD(fresh.parameters, lr=header["lr"])
+    got = [train_step(fresh, loss_fn, opt2, X, T, wl.pred_map, wl.squeeze_dim).item() for _ in range(3)]
+    assert got == want
+    for p, w in zip(fresh.parameters(), final):
+        np.testing.assert_array_equal(p.data, w)
+
+    other = nn.Sequential(nn.Linear(2, 8), Tanh())
+    with pytest.raises(KeyError):
+        ck.load_checkpoint(path, other)
+    bad = nn.Sequential(nn.Linear(2, 64), Tanh(), nn.Linear(64, 31), Tanh(), nn.Linear(32, 16), Tanh(), nn.Linear(16, 1), Tanh())
+    with pytest.raises(ValueError):
+        ck.load_checkpoint(path, bad)
+    with pytest.raises(FileNotFoundError):
+        ck.load_checkpoint(tmp_path / "absent.npz", fresh)
+    junk = tmp_path / "junk.npz"
+    junk.write_bytes(b"not a checkpoint")
+    with pytest.raises(ValueError):
+        ck.load_checkpoint(junk, fresh)

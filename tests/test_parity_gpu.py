@@ -410,6 +410,33 @@ def test_graphed_training_step_matches_eager_and_notebook(mt):
     step.close()
 
 
+def test_max_min_reductions_on_cuda_match_cpu_path(mt):
+    """Section 8(f) item 2: Reduce.max / Reduce.min (reference reduce.py:46-105) on the device - forward bit-exact,
+    backward (gradient shared between ties) bit-exact against this package's CPU path."""
+    from microtorch_b200.tensor.ops.reduce import Reduce
+    rng = np.random.default_rng(33)
+    xv = rng.standard_normal((37, 130)).astype(np.float32)
+    xv[3, 7] = xv[3, 100] = xv.max() + 1.0                                      # a tie for the global / row maximum
+    xv[5, 0] = xv[9, 0] = xv.min() - 1.0
+    cases = [(None, False), (0, True), (1, True), (0, False), (-1, True)]
+    for name in ("max", "min"):
+        for axis, keep in cases:
+            res = []
+            for dev in ("cpu", "cuda"):
+                x = mt.Tensor(xv, requires_grad=True, device=dev)
+                # the reference's Tensor exposes .max() only; Reduce.min is reached through from_props
+                r = x.max(axis=axis, keepdims=keep) if name == "max" else mt.Tensor.from_props(Reduce.min(x, axis, keep))
+                w = np.linspace(0.5, 1.5, r.size, dtype=np.float32).reshape(r.shape)
+                (r * mt.Tensor(w, device=dev)).sum().backward()
+                res.append((host(r.data), host(x.grad)))
+            np.testing.assert_array_equal(res[0][0], res[1][0])
+            np.testing.assert_array_equal(res[0][1], res[1][1])
+            np.testing.assert_array_equal(res[1][0], getattr(np, name)(xv, axis=axis, keepdims=keep))
+    big = rng.standard_normal((1 << 22,)).astype(np.float32)
+    t = mt.Tensor(big, device="cuda")
+    assert t.max().item() == big.max() and mt.Tensor.from_props(Reduce.min(t, None)).item() == big.min()
+
+
 def test_select_family_and_l1loss_on_cuda_match_cpu_path(mt):
     """Section 8(f) item 3: comparisons / where / abs / maximum / minimum / threshold / masked_fill / sign / clip /
     L1Loss / clip_grad(_norm) on the device, bit-exact against this package's CPU path (which passes the reference's
@@ -611,3 +638,54 @@ def test_inplace_ops_on_cuda(mt):
     assert host(base.data).shape == (12, 20)
     col = host(view.data) - xv.T
     assert np.allclose(col, col[:, :1])                            # one value per row of the view was added
+
+
+def test_checkpoint_resume_on_cuda_is_bit_exact(mt, tmp_path):
+    """save after 2 device steps, then (a) load into a fresh host-side model that migrates on its
+    first forward and (b) load IN PLACE into an already-migrated device model: both continue the original trajectory
+    bit-exactly, and a state saved from the device loads into the CPU path."""
+    from microtorch_b200 import checkpoint as ck, workloads as W
+    from microtorch_b200.trainer import train_step
+    wl = W.scaled(W.C2, 256, (64, 128, 96, 10))
+    loss_fn = mt.losses[wl.loss]()
+
+    def make():
+        model, x, t = W.setup(wl, mt.Linear, mt.Tanh, mt.Sequential)
+        return model, mt.Tensor(x, device="cuda"), mt.Tensor(t, device="cuda")
+
+    def steps(model, X, T, n):
+        opt = mt.SGD(model.parameters, lr=wl.lr)
+        return [train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim).item() for _ in range(n)]
+
+    model, X, T = make()
+    steps(model, X, T, 2)
+    path = tmp_path / "c2_small.npz"
+    ck.save_checkpoint(path, model, step=2, lr=wl.lr)
+    want = steps(model, X, T, 3)
+    final = [host(p.data) for p in model.parameters()]
+
+    fresh, _, _ = make()                                    # (a) parameters still on the host
+    assert ck.load_checkpoint(path, fresh)["step"] == 2
+    assert steps(fresh, X, T, 3) == want
+    for p, w in zip(fresh.parameters(), final):
+        np.testing.assert_array_equal(host(p.data), w)
+
+    moved, _, _ = make()                                    # (b) already on the device: load in place
+    steps(moved, X, T, 1)
+    held = [p.data.ptr for p in moved.parameters()]
+    ck.load_checkpoint(path, moved)
+    assert [p.data.ptr for p in moved.parameters()] == held
+    assert steps(moved, X, T, 3) == want
+
+    cpu_model, x, t = W.setup(wl, mt.Linear, mt.Tanh, mt.Sequential)      # device state -> CPU path
+    ck.load_state_dict(cpu_model, ck.state_dict(model))
+    for p, w in zip(cpu_model.parameters(), final):
+        np.testing.assert_array_equal(p.data, w)
+
+    t0 = mt.Tensor(np.arange(12, dtype=np.float32).reshape(3, 4), requires_grad=True, device="cuda")
+    (t0 * t0).sum().backward()
+    t0.save(tmp_path / "t.pkl")                              # the reference's own single-tensor format
+    t1 = mt.Tensor.load(tmp_path / "t.pkl")
+    assert t1.device.value == "cuda" and t1.requires_grad
+    np.testing.assert_array_equal(host(t1.data), host(t0.data))
+    np.testing.assert_array_equal(host(t1.grad), host(t0.grad))

@@ -23,9 +23,10 @@ namespace {
 constexpr int THREADS = 512;
 constexpr int RB = 4;                       // rows per warp iteration (register blocking over the smem-resident W)
 constexpr int SMEM_W_MAX = 200 * 1024;
+int g_skinny_ring = 1;                      // dW: 1 = cp.async ring, 0 = register double buffer (mt_gemm_set_skinny_ring)
 
-__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+__device__ __forceinline__ float dot4_acc(const float4 a, const float4 b, float c) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, c))));
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -49,25 +50,28 @@ __global__ void __launch_bounds__(THREADS) skinny_fwd_kernel(float* __restrict__
     for (int i = 0; i < RB; ++i)
 #pragma unroll
       for (int n = 0; n < NP; ++n) acc[i][n] = 0.f;
-    // two column chunks per iteration: 2*RB independent 128-bit loads in flight per lane
-    for (int c = lane; c < K4; c += 64) {
-      float4 x[2][RB];
-      const bool second = (c + 32 < K4);
+    // software pipeline: the loads of chunk c+32 are issued before the FMAs of chunk c, so every warp keeps RB
+    // 128-bit loads in flight while it computes (the smem-resident W costs one LDS.128 per 4*RB FMAs)
+    float4 xc[RB];
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+    for (int i = 0; i < RB; ++i)
+      xc[i] = (r0 + i < M && lane < K4) ? mtd::ld_stream4(X + (r0 + i) * ldx + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = lane; c < K4; c += 32) {
+      float4 xn[RB];
+      const bool more = (c + 32 < K4);
 #pragma unroll
-        for (int i = 0; i < RB; ++i)
-          x[h][i] = (r0 + i < M && (h == 0 || second)) ? mtd::ld_stream4(X + (r0 + i) * ldx + 4 * (c + 32 * h))
-                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < RB; ++i)
+        xn[i] = (more && r0 + i < M) ? mtd::ld_stream4(X + (r0 + i) * ldx + 4 * (c + 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int n = 0; n < NP; ++n) {
         if (n < N) {
-          const float4 w0 = Ws[n * K4 + c];
-          const float4 w1 = second ? Ws[n * K4 + c + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 w = Ws[n * K4 + c];
 #pragma unroll
-          for (int i = 0; i < RB; ++i) acc[i][n] += dot4(x[0][i], w0) + dot4(x[1][i], w1);
+          for (int i = 0; i < RB; ++i) acc[i][n] = dot4_acc(xc[i], w, acc[i][n]);   // 4 FMAs, no separate add
         }
       }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) xc[i] = xn[i];
     }
 #pragma unroll
     for (int i = 0; i < RB; ++i)
@@ -91,6 +95,18 @@ __global__ void __launch_bounds__(THREADS) skinny_fwd_kernel(float* __restrict__
   }
 }
 
+// per-thread asynchronous prefetch queue: 16-byte cp.async (L2 -> shared, no registers held while in flight).
+// Every thread reads back only the slots it filled itself, so no barrier is needed around the ring.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int bytes /* 16, or 0 = zero-fill */) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+constexpr int DW_STAGES = 4;                // ring depth of skinny_dw_ring_kernel (one X row slice per stage)
+
 // ------------------------------------------------------------------------------------------------ dX
 template <int NP>
 __global__ void __launch_bounds__(THREADS) skinny_dx_kernel(float* __restrict__ dX, const float* __restrict__ dZ,
@@ -113,7 +129,18 @@ __global__ void __launch_bounds__(THREADS) skinny_dx_kernel(float* __restrict__ 
 #pragma unroll
       for (int n = 0; n < NP; ++n) dz[i][n] = __shfl_sync(0xffffffffu, mine, n);
     }
+    float4 tc[RB];                         // saved activations of chunk c (tanh' epilogue), loaded one chunk ahead
+#pragma unroll
+    for (int i = 0; i < RB; ++i)
+      tc[i] = (epi_tanh && r0 + i < M && lane < K4) ? mtd::ld_stream4(epi_tanh + (r0 + i) * K + 4 * lane)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = lane; c < K4; c += 32) {
+      float4 tn[RB];
+      const bool more = epi_tanh && (c + 32 < K4);
+#pragma unroll
+      for (int i = 0; i < RB; ++i)
+        tn[i] = (more && r0 + i < M) ? mtd::ld_stream4(epi_tanh + (r0 + i) * K + 4 * (c + 32))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 o[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -135,7 +162,7 @@ __global__ void __launch_bounds__(THREADS) skinny_dx_kernel(float* __restrict__ 
         if (r0 + i < M) {
           float4 v = o[i];
           if (epi_tanh) {
-            const float4 t = mtd::ld_stream4(epi_tanh + (r0 + i) * K + 4 * c);
+            const float4 t = tc[i];
             v.x = __fmul_rn(v.x, __fsub_rn(1.f, __fmul_rn(t.x, t.x)));
             v.y = __fmul_rn(v.y, __fsub_rn(1.f, __fmul_rn(t.y, t.y)));
             v.z = __fmul_rn(v.z, __fsub_rn(1.f, __fmul_rn(t.z, t.z)));
@@ -144,6 +171,8 @@ __global__ void __launch_bounds__(THREADS) skinny_dx_kernel(float* __restrict__ 
           mtd::st4(dX + (r0 + i) * K + 4 * c, v);
         }
       }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) tc[i] = tn[i];
     }
   }
 }
@@ -173,23 +202,103 @@ __global__ void __launch_bounds__(THREADS) skinny_dw_kernel(float* __restrict__ 
       dzs[r][n] = (r < rows && n < N) ? __ldg(dZ + (mb + r) * ldz + n) : 0.f;
     }
     __syncthreads();
+    float4 xc[CG];                         // row r of this thread's columns, loaded one row ahead of its FMAs
+#pragma unroll
+    for (int g = 0; g < CG; ++g) {
+      const int c = threadIdx.x + g * THREADS;
+      xc[g] = (c < K4) ? mtd::ld_stream4(X + mb * ldx + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll 2
     for (int r = 0; r < rows; ++r) {
-      float4 x[CG];
+      float4 xn[CG];
 #pragma unroll
       for (int g = 0; g < CG; ++g) {
         const int c = threadIdx.x + g * THREADS;
-        x[g] = (c < K4) ? mtd::ld_stream4(X + (mb + r) * ldx + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xn[g] = (c < K4 && r + 1 < rows) ? mtd::ld_stream4(X + (mb + r + 1) * ldx + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int n = 0; n < NP; ++n) {
         const float d = dzs[r][n];          // broadcast read
 #pragma unroll
         for (int g = 0; g < CG; ++g) {
-          acc[g][n].x = fmaf(d, x[g].x, acc[g][n].x);
-          acc[g][n].y = fmaf(d, x[g].y, acc[g][n].y);
-          acc[g][n].z = fmaf(d, x[g].z, acc[g][n].z);
-          acc[g][n].w = fmaf(d, x[g].w, acc[g][n].w);
+          acc[g][n].x = fmaf(d, xc[g].x, acc[g][n].x);
+          acc[g][n].y = fmaf(d, xc[g].y, acc[g][n].y);
+          acc[g][n].z = fmaf(d, xc[g].z, acc[g][n].z);
+          acc[g][n].w = fmaf(d, xc[g].w, acc[g][n].w);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < CG; ++g) xc[g] = xn[g];
+    }
+  }
+  float* out = partial + (long long)blockIdx.x * N * K;
+#pragma unroll
+  for (int g = 0; g < CG; ++g) {
+    const int c = threadIdx.x + g * THREADS;
+    if (c < K4) {
+#pragma unroll
+      for (int n = 0; n < NP; ++n)
+        if (n < N) mtd::st4(out + (long long)n * K + 4 * c, acc[g][n]);
+    }
+  }
+}
+
+// dW with the X rows staged through a cp.async ring (DW_STAGES rows of this CTA's column slice, private slots per
+// thread): DW_STAGES-1 rows stay in flight while one row is folded into the accumulators.
+template <int NP, int CG>
+__global__ void __launch_bounds__(THREADS) skinny_dw_ring_kernel(float* __restrict__ partial, const float* __restrict__ dZ,
+                                                                 const float* __restrict__ X, long long M, int N, long long K,
+                                                                 long long ldz, long long ldx, long long slab) {
+  __shared__ float dzs[DZ_ROWS][NP];
+  extern __shared__ float4 ringbuf[];       // [stage][CG][THREADS]
+  const int K4 = (int)(K >> 2);
+  const long long m_begin = (long long)blockIdx.x * slab;
+  const long long m_end = m_begin + slab < M ? m_begin + slab : M;
+  const long long total = m_end - m_begin;
+  float4 acc[CG][NP];
+#pragma unroll
+  for (int g = 0; g < CG; ++g)
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[g][n] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto issue = [&](long long q, int stage) {
+#pragma unroll
+    for (int g = 0; g < CG; ++g) {
+      const int c = threadIdx.x + g * THREADS;
+      const bool ok = c < K4;
+      cp_async16(ringbuf + (stage * CG + g) * THREADS + threadIdx.x, ok ? X + (m_begin + q) * ldx + 4 * c : X, ok ? 16 : 0);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < DW_STAGES; ++s) {
+    if (s < total) issue(s, s);
+    cp_async_commit();
+  }
+  long long q = 0;
+  for (long long mb = m_begin; mb < m_end; mb += DZ_ROWS) {
+    const int rows = (int)(m_end - mb < DZ_ROWS ? m_end - mb : DZ_ROWS);
+    __syncthreads();
+    for (int i = threadIdx.x; i < DZ_ROWS * NP; i += THREADS) {
+      const int r = i / NP, n = i - r * NP;
+      dzs[r][n] = (r < rows && n < N) ? __ldg(dZ + (mb + r) * ldz + n) : 0.f;
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; ++r, ++q) {
+      const int stage = (int)(q % DW_STAGES);
+      cp_async_wait<DW_STAGES - 1>();
+      float4 xc[CG];
+#pragma unroll
+      for (int g = 0; g < CG; ++g) xc[g] = ringbuf[(stage * CG + g) * THREADS + threadIdx.x];
+      if (q + DW_STAGES < total) issue(q + DW_STAGES, stage);
+      cp_async_commit();
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const float d = dzs[r][n];          // broadcast read
+#pragma unroll
+        for (int g = 0; g < CG; ++g) {
+          acc[g][n].x = fmaf(d, xc[g].x, acc[g][n].x);
+          acc[g][n].y = fmaf(d, xc[g].y, acc[g][n].y);
+          acc[g][n].z = fmaf(d, xc[g].z, acc[g][n].z);
+          acc[g][n].w = fmaf(d, xc[g].w, acc[g][n].w);
         }
       }
     }
@@ -211,10 +320,10 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 template <int NP>
 int run_fwd(const GemmArgs& a, long long ldx, long long ldw) {
   const size_t smem = (size_t)a.N * a.K * 4;
+  const int grid = (int)std::min<long long>(g().sm_count, ceil_div(a.M, (THREADS / 32) * RB));
   auto kern = skinny_fwd_kernel<NP>;
   static bool set = false;
   if (!set) { MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_MAX)); set = true; }
-  const int grid = (int)std::min<long long>(g().sm_count, ceil_div(a.M, (THREADS / 32) * RB));
   kern<<<grid, THREADS, smem, g().stream>>>(a.C, a.A, a.B, a.bias, a.M, (int)a.N, a.K, ldx, ldw, a.act);
   MT_LAUNCHED();
   return MT_OK;
@@ -245,14 +354,32 @@ int run_dw(const GemmArgs& a, long long ldz, long long ldx) {
   float* partial = nullptr;
   int rc = pool_alloc((void**)&partial, sizeof(float) * (size_t)ctas * a.M * Kc);
   if (rc) return rc;
+  if (g_skinny_ring) {
+#define MT_DWR(CGV)                                                                                                    \
+  do {                                                                                                                 \
+    auto kern = skinny_dw_ring_kernel<NP, CGV>;                                                                        \
+    const size_t ring = (size_t)DW_STAGES * CGV * THREADS * sizeof(float4);                                           \
+    static bool set = false;                                                                                           \
+    if (!set) { MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring)); set = true; } \
+    kern<<<(int)ctas, THREADS, ring, g().stream>>>(partial, a.A, a.B, rows, (int)a.M, Kc, ldz, ldx, slab);             \
+  } while (0)
+    switch (cg) {
+      case 1: MT_DWR(1); break;
+      case 2: MT_DWR(2); break;
+      case 3: MT_DWR(3); break;
+      default: MT_DWR(4); break;
+    }
+#undef MT_DWR
+  } else {
 #define MT_DW(CGV) skinny_dw_kernel<NP, CGV><<<(int)ctas, THREADS, 0, g().stream>>>(partial, a.A, a.B, rows, (int)a.M, Kc, ldz, ldx, slab)
-  switch (cg) {
-    case 1: MT_DW(1); break;
-    case 2: MT_DW(2); break;
-    case 3: MT_DW(3); break;
-    default: MT_DW(4); break;
-  }
+    switch (cg) {
+      case 1: MT_DW(1); break;
+      case 2: MT_DW(2); break;
+      case 3: MT_DW(3); break;
+      default: MT_DW(4); break;
+    }
 #undef MT_DW
+  }
   MT_LAUNCHED();
   rc = splitk_finalize(a.C, partial, (int)ctas, a.M, Kc, nullptr, MT_ACT_NONE, a.accumulate, nullptr);
   pool_free(partial);
@@ -303,3 +430,10 @@ int gemm_skinny_try(const GemmArgs& a) {
 }
 
 }  // namespace mt
+
+// tuning knob (tools/, tests): dW kernel with the cp.async ring (1, default) or the register double buffer (0).
+// (The same ring was tried for the forward kernel: 0.43 ms against 0.29 ms for the register double buffer, dropped.)
+extern "C" __attribute__((visibility("default"))) int mt_gemm_set_skinny_ring(int v) {
+  g_skinny_ring = v ? 1 : 0;
+  return MT_OK;
+}

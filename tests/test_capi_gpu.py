@@ -313,11 +313,14 @@ def test_pool_reuses_blocks(lib):
     b.free()
 
 
-@pytest.mark.parametrize("M,N,K", [(4096, 10, 4096), (1000, 3, 256), (2048, 16, 1024), (777, 7, 512)])
+@pytest.mark.parametrize("M,N,K", [(4096, 10, 4096), (1000, 3, 256), (2048, 16, 1024), (777, 7, 512), (1001, 10, 1100),
+                                   (258, 12, 132), (5000, 10, 2048)])
 def test_skinny_head_kernels_match_generic_tile_and_float64(lib, M, N, K):
     """The HBM-bound tiny-N kernels (4096->10 head) against float64 and against the generic SIMT tile,
-    including the dX epilogue that emits the producer's pre-activation gradient."""
+    including the dX epilogue that emits the producer's pre-activation gradient.  Both prefetch schemes
+    (cp.async ring / register double buffer) are run; ragged row blocks and column chunks included."""
     lib.mt_gemm_set_skinny.argtypes = [C.c_int]
+    lib.mt_gemm_set_skinny_ring.argtypes = [C.c_int]
     rng = np.random.default_rng(12)
     X = np.tanh(rng.standard_normal((M, K))).astype(np.float32)       # a tanh output, as in a hidden layer
     W = (rng.standard_normal((N, K)) * 0.1).astype(np.float32)
@@ -325,19 +328,25 @@ def test_skinny_head_kernels_match_generic_tile_and_float64(lib, M, N, K):
     dY = rng.standard_normal((M, N)).astype(np.float32)
     Xd, Wd, bd, dYd = Dev(X), Dev(W), Dev(b), Dev(dY)
     outs = {}
-    for skinny in (1, 0):
-        lib.mt_gemm_set_skinny(skinny)
-        Y = Dev(shape=(M, N))
-        _capi.check(lib.mt_linear_fwd_f32(Y.ptr, Xd.ptr, Wd.ptr, bd.ptr, M, N, K, 1))
-        dX, dW = Dev(shape=(M, K)), Dev(np.ones((N, K), np.float32))
-        _capi.check(lib.mt_linear_bwd_f32(dX.ptr, dW.ptr, dYd.ptr, Y.ptr, Xd.ptr, Wd.ptr, M, N, K, 1 | 2))
-        outs[skinny] = (Y.get(), dX.get(), dW.get())
-    lib.mt_gemm_set_skinny(1)
+    try:
+        for mode, (skinny, ring) in {"ring": (1, 1), "regs": (1, 0), "generic": (0, 1)}.items():
+            lib.mt_gemm_set_skinny(skinny)
+            lib.mt_gemm_set_skinny_ring(ring)
+            Y = Dev(shape=(M, N))
+            _capi.check(lib.mt_linear_fwd_f32(Y.ptr, Xd.ptr, Wd.ptr, bd.ptr, M, N, K, 1))
+            dX, dW = Dev(shape=(M, K)), Dev(np.ones((N, K), np.float32))
+            _capi.check(lib.mt_linear_bwd_f32(dX.ptr, dW.ptr, dYd.ptr, Y.ptr, Xd.ptr, Wd.ptr, M, N, K, 1 | 2))
+            outs[mode] = (Y.get(), dX.get(), dW.get())
+    finally:
+        lib.mt_gemm_set_skinny(1)
+        lib.mt_gemm_set_skinny_ring(1)
     Yr = np.tanh(X.astype(np.float64) @ W.astype(np.float64).T + b)
-    dz = dY.astype(np.float64) * (1 - outs[1][0].astype(np.float64) ** 2)
+    dz = dY.astype(np.float64) * (1 - outs["ring"][0].astype(np.float64) ** 2)
     dXr = (dz @ W) * (1 - X.astype(np.float64) ** 2)
     dWr = dz.T @ X + 1.0
-    for got in (outs[1], outs[0]):
+    for got in outs.values():
         assert gemm_err(got[0], Yr) < 1e-5
         assert gemm_err(got[1], dXr) < 1e-5
         assert gemm_err(got[2], dWr) < 1e-5
+    np.testing.assert_array_equal(outs["ring"][0], outs["regs"][0])      # same summation order in both schemes
+    np.testing.assert_array_equal(outs["ring"][2], outs["regs"][2])

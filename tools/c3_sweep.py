@@ -72,9 +72,12 @@ def main():
                 x.zero_grad(); y.zero_grad()
                 z = x * y + x ** 2 - y
                 z.sum().backward()
-            # fwd: mul (2B+m), pow (2B), add (3B), neg(m) , add (2B+m) ; sum (B)
-            # bwd: x.grad = g*y [from mul] (B + m) + g*2x [pow'] (2B) accumulate (3B) ; passes for y: reduce(g*x) (B..2B), reduce(-g)
-            bytes_alg = (2 * B + m) + 2 * B + 3 * B + 2 * m + (2 * B + m) + B + (B + m + B) + 2 * B + 3 * B + (2 * B if tag == "same" else B + m) + m
+            # fwd: mul (2B+m), pow (2B), add (3B), neg (2m), add (2B+m), sum (B)
+            # bwd (g = dL/dz is a stride-0 view of one scalar, never materialised): pow' g*2x (2B); x.grad += g*y
+            #      (read y m, write B; accumulate 3B); y.grad: same-shape g*x (2B) + accumulate (2B), broadcast y:
+            #      one read of x (B) folded to m elements
+            bytes_alg = ((2 * B + m) + 2 * B + 3 * B + 2 * m + (2 * B + m) + B) + 2 * B + (m + B) + 3 * B \
+                + (4 * B if tag == "same" else B + m)
             work[f"poly_{tag}"] = (poly, bytes_alg)
 
         def f_log():

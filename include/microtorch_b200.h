@@ -235,6 +235,33 @@ int mt_loss_fwd_bwd_f32(int kind, float* loss_out, float* dpred_or_null, const f
 int mt_sgd_multi_f32(float* const* params, float* const* grads, const size_t* sizes, int count,
                      float lr, int zero_grads);
 
+/* ---------------------------------------------------------------- whole-loop fusion */
+/* `steps` full training steps of a small Linear(+Tanh) stack in ONE launch: weights, activations and
+ * gradients stay in the shared memory of one CTA; per step HBM receives one loss value.
+ *     for k in range(steps): model.zero_grad(); pred = model(X) [* pred_scale + pred_shift];
+ *                            loss = loss_fn(pred, T); loss.backward(); optimizer.step()
+ * replaces: the user loop demo.ipynb:5178-5189 over Sequential.forward (src/nn/sequential.py:37-48),
+ * Linear.forward (src/nn/layer/linear.py:48-62), Tanh (src/nn/activation.py:11-12), Loss.forward
+ * (src/nn/loss.py:35-100), Tensor.backward (src/tensor/tensor.py:256-283) and SGD.step
+ * (src/nn/optimizer.py:37-39), for full-batch X [batch, dims[0]] / T [batch * dims[n_layers]] that do
+ * not change between steps.  weight[i] is [dims[i+1], dims[i]] row-major and is updated in place;
+ * bias[i] (may be NULL) is read only - the reference gives biases no gradient (in-place add).
+ * grad_weight[i] (may be NULL) receives the LAST step's dL/dW_i, what Parameter.grad holds after the loop.
+ * losses[k] = loss of step k (device array of `steps` floats).  loss_scale = float32(1/element count).
+ * MT_ERR_UNSUPPORTED when model + batch exceed the 227 KB of one CTA: use the per-step path then.       */
+#define MT_MLP_MAX_LAYERS 8
+typedef struct mt_mlp_desc {
+  int32_t n_layers;
+  int32_t dims[MT_MLP_MAX_LAYERS + 1];
+  int32_t act[MT_MLP_MAX_LAYERS];              /* mt_act after layer i */
+  float* weight[MT_MLP_MAX_LAYERS];
+  const float* bias[MT_MLP_MAX_LAYERS];
+  float* grad_weight[MT_MLP_MAX_LAYERS];
+} mt_mlp_desc;
+int mt_mlp_fit_f32(const mt_mlp_desc* desc, const float* X, const float* T, int64_t batch, int loss_kind,
+                   int has_pred_map, float pred_scale, float pred_shift, float lr, float loss_scale, int steps,
+                   float* losses);
+
 /* ---------------------------------------------------------------- collective ------ */
 /* Data-parallel gradient exchange (no counterpart in the reference: new component,
  * SURVEY.md section 8(e)).  NCCL is dlopen()ed from `libnccl_path` (NULL = "libnccl.so.2"). */

@@ -31,6 +31,7 @@ SOURCES = [
     "mt_gemm_skinny.cu",
     "mt_gemm_tc.cu",
     "mt_linear.cu",
+    "mt_mlp_small.cu",
     "mt_comm.cu",
 ]
 

@@ -23,6 +23,16 @@ c_u64p = C.POINTER(C.c_uint64)
 c_voidpp = C.POINTER(C.c_void_p)
 VP = C.c_void_p
 
+MLP_MAX_LAYERS = 8
+
+
+class MlpDesc(C.Structure):
+    """mt_mlp_desc of the header."""
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MLP_MAX_LAYERS + 1)), ("act", C.c_int32 * MLP_MAX_LAYERS),
+                ("weight", C.c_void_p * MLP_MAX_LAYERS), ("bias", C.c_void_p * MLP_MAX_LAYERS),
+                ("grad_weight", C.c_void_p * MLP_MAX_LAYERS)]
+
+
 # name -> (argtypes, doc)   every symbol include/microtorch_b200.h declares
 PROTOTYPES = {
     "mt_device_count": [C.POINTER(C.c_int)],
@@ -80,6 +90,8 @@ PROTOTYPES = {
     "mt_gemm_set_engine": [C.c_int],
     "mt_loss_fwd_bwd_f32": [C.c_int, VP, VP, VP, VP, C.c_size_t, C.c_float],
     "mt_sgd_multi_f32": [c_voidpp, c_voidpp, c_sizep, C.c_int, C.c_float, C.c_int],
+    "mt_mlp_fit_f32": [C.POINTER(MlpDesc), VP, VP, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                       C.c_int, VP],
     "mt_comm_load": [C.c_char_p],
     "mt_comm_unique_id": [C.c_char_p],
     "mt_comm_init_rank": [C.c_char_p, C.c_int, C.c_int],
@@ -97,6 +109,7 @@ BIN_LT, BIN_GT, BIN_LE, BIN_GE, BIN_EQ, BIN_NE, BIN_MAX, BIN_MIN = range(7, 15)
 UN_NEG, UN_LOG, UN_TANH, UN_EXP, UN_POW, UN_SCALE, UN_ADDS, UN_ABS = range(8)
 ACT_NONE, ACT_TANH = 0, 1
 LOSS_MSE, LOSS_CE_REF, LOSS_BCE = 0, 1, 2
+ERR_UNSUPPORTED = 6
 
 
 class MicrotorchB200Error(RuntimeError):

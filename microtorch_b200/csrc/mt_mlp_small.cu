@@ -1,0 +1,415 @@
+// mt_mlp_small.cu - the whole training loop of a small Linear(+Tanh) stack in ONE kernel launch.
+//
+// Reference path: the user loop of demo.ipynb:5178-5189 -
+//     for k in range(steps): model.zero_grad(); pred = model(X); loss = loss_fn(pred, T); loss.backward(); opt.step()
+// with full-batch X / T that never change (src/nn/sequential.py:37-48, src/nn/layer/linear.py:48-62,
+// src/nn/loss.py:35-100, src/nn/optimizer.py:37-39).  At the notebook's sizes (200 samples, 2->64->32->16->1) one step
+// is ~1.6 MFLOP: every launch-per-op or even graph-per-step scheme is pure launch/dependency latency (SURVEY.md
+// section 8f item 1).  Here a thread-block CLUSTER (up to 8 CTAs on 8 SMs) keeps weights, activations and gradients
+// in shared memory and iterates the steps on chip; HBM sees the inputs once, one loss value per step, and the final
+// weights / last gradients.  The batch rows are split over the CTAs (data parallel inside the cluster), every CTA
+// holds a full replica of the weights, and the only exchange per step is the sum of the per-CTA partial dW (and
+// partial loss) read from the peers' shared memory (DSMEM) after ONE cluster barrier.
+//
+// Per step (phases separated by __syncthreads, rows = this CTA's share of the batch):
+//   forward   A_i = tanh(A_{i-1} W_i^T + b_i)                         i = 1..L
+//   loss      partial value (block sum) and G_L = dL/dZ_L written in place over A_L (pred map a*y+b, tanh' folded in)
+//   backward  partial dW_i = G_i^T A_{i-1} -> scratch;  G_{i-1} = (G_i W_i) * (1 - A_{i-1}^2) in place over A_{i-1}
+//   exchange  barrier.cluster; every CTA adds the C partials in rank order (identical sums everywhere) and applies
+//             W_i = W_i - lr * dW_i  (two roundings, like NumPy).  The scratch is double buffered, so one barrier
+//             per step is enough.
+// Biases receive no gradient in the reference and stay constant.
+//
+// The three matrix products of a layer run through one register-tiled routine (block_gemm): TMxTN outputs per
+// work item, the reduction split over R lanes of a warp (shuffle fold) so that tiny layers still fill the CTA.
+// All shared-memory pitches are odd, which keeps every access pattern of the three products conflict-free or
+// broadcast.  Deterministic: fixed work decomposition, no atomics.
+#include <algorithm>
+
+#include "mt_common.cuh"
+#include "mt_loss.cuh"
+
+using namespace mt;
+
+namespace {
+
+constexpr int THREADS = 1024;
+constexpr int MAXL = MT_MLP_MAX_LAYERS;
+constexpr int SMEM_MAX = 227 * 1024 - 256;   // dynamic part: the CTA limit minus this kernel's static shared memory
+
+struct Phase {            // one matrix product: tile shape code (0: 4x4, 1: 2x2, 2: 1x1) and lanes per work item
+  int tile, R;
+};
+
+struct Params {
+  int L, B, steps, loss_kind, has_map;
+  int rows_per;               // batch rows per CTA of the cluster
+  float pa, pb, lr, scale;
+  int d[MAXL + 1], act[MAXL];
+  int pA[MAXL + 1], pW[MAXL];
+  int offA[MAXL + 1], offW[MAXL], offB[MAXL], offT;
+  int offS[2], offSW[MAXL], offSL;   // two scratch buffers; inside one: partial dW of layer i, then the partial loss
+  Phase fwd[MAXL], dw[MAXL], dx[MAXL];
+  float* W[MAXL];
+  const float* bias[MAXL];
+  float* gradW[MAXL];
+  const float* X;
+  const float* T;
+  float* losses;
+};
+
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_size() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read one float of CTA `rank`'s shared memory at the address that `local` has in this CTA
+__device__ __forceinline__ float ld_peer(const float* local, unsigned rank) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(local);
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ float block_sum_rt(float v, float* red) {      // blockDim.x threads; ends with a barrier
+  v = mtd::warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < nw; ++w) t += red[w];                                // fixed order, same value in every thread
+  __syncthreads();
+  return t;
+}
+
+// C[m,n] = sum_k A[m*a_sm + k*a_sk] * B[k*b_sk + n*b_sn], delivered to epi(m, n, value).
+// Work item = TMxTN outputs {tm + i*MT} x {tn + j*NT} (strided so neighbouring lanes touch neighbouring n);
+// R lanes share an item and split k.
+template <int TM, int TN, class Epi>
+__device__ __forceinline__ void block_gemm(int M, int N, int K, const float* __restrict__ A, int a_sm, int a_sk,
+                                           const float* __restrict__ Bm, int b_sk, int b_sn, int R, Epi epi) {
+  const int MT = (M + TM - 1) / TM, NT = (N + TN - 1) / TN;
+  const int items = MT * NT;
+  const int r = threadIdx.x & (R - 1);
+  const int per_pass = (int)blockDim.x / R;
+  // every lane of a warp runs the same number of passes (items are padded), so the shuffles below are convergent
+  const int passes = (items + per_pass - 1) / per_pass;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int item = pass * per_pass + threadIdx.x / R;
+    const bool live = item < items;
+    const int tm = live ? item / NT : 0, tn = live ? item - (item / NT) * NT : 0;
+    int am[TM], bn[TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) am[i] = min(tm + i * MT, M - 1) * a_sm;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bn[j] = min(tn + j * NT, N - 1) * b_sn;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    if (live) {
+#pragma unroll 4
+      for (int k = r; k < K; k += R) {
+        float a[TM], b[TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) a[i] = A[am[i] + k * a_sk];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) b[j] = Bm[k * b_sk + bn[j]];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+    for (int o = R >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], o);
+    }
+    if (live && r == 0) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          const int m = tm + i * MT, n = tn + j * NT;
+          if (m < M && n < N) epi(m, n, acc[i][j]);
+        }
+    }
+  }
+}
+
+template <class Epi>
+__device__ __forceinline__ void run_gemm(Phase ph, int M, int N, int K, const float* A, int a_sm, int a_sk, const float* Bm,
+                                         int b_sk, int b_sn, Epi epi) {
+  switch (ph.tile) {
+    case 0: block_gemm<4, 4>(M, N, K, A, a_sm, a_sk, Bm, b_sk, b_sn, ph.R, epi); break;
+    case 1: block_gemm<2, 2>(M, N, K, A, a_sm, a_sk, Bm, b_sk, b_sn, ph.R, epi); break;
+    default: block_gemm<1, 1>(M, N, K, A, a_sm, a_sk, Bm, b_sk, b_sn, ph.R, epi); break;
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(THREADS, 1) mlp_fit_kernel(const __grid_constant__ Params p) {
+  extern __shared__ float sm[];
+  __shared__ float red[THREADS / 32];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int L = p.L;
+  const unsigned rank = cluster_rank(), csize = cluster_size();
+  const int r_begin = (int)rank * p.rows_per;
+  const int B = max(0, min(p.rows_per, p.B - r_begin));       // rows of this CTA
+  // ---- stage weights and biases (full replica), this CTA's rows of X and T
+  for (int i = 0; i < L; ++i) {
+    const int dout = p.d[i + 1], din = p.d[i];
+    for (int e = tid; e < dout * din; e += nthr) {
+      const int n = e / din, k = e - n * din;
+      sm[p.offW[i] + n * p.pW[i] + k] = p.W[i][e];
+    }
+    for (int e = tid; e < dout; e += nthr) sm[p.offB[i] + e] = p.bias[i] ? p.bias[i][e] : 0.f;
+  }
+  for (int e = tid; e < B * p.d[0]; e += nthr) {
+    const int b = e / p.d[0], k = e - b * p.d[0];
+    sm[p.offA[0] + b * p.pA[0] + k] = p.X[(size_t)r_begin * p.d[0] + e];
+  }
+  const int nout = B * p.d[L];
+  for (int e = tid; e < nout; e += nthr) sm[p.offT + e] = p.T[(size_t)r_begin * p.d[L] + e];
+  __syncthreads();
+
+  for (int step = 0; step < p.steps; ++step) {
+    float* S = sm + p.offS[step & 1];
+    // ---- forward
+    for (int i = 0; i < L; ++i) {
+      const float* Ain = sm + p.offA[i];
+      float* Aout = sm + p.offA[i + 1];
+      const float* bias = sm + p.offB[i];
+      const int po = p.pA[i + 1], act = p.act[i];
+      run_gemm(p.fwd[i], B, p.d[i + 1], p.d[i], Ain, p.pA[i], 1, sm + p.offW[i], 1, p.pW[i],
+               [=](int b, int n, float v) {
+                 v = __fadd_rn(v, bias[n]);
+                 Aout[b * po + n] = act ? tanhf(v) : v;
+               });
+      __syncthreads();
+    }
+    // ---- partial loss value + dL/dZ_L in place
+    {
+      float* AL = sm + p.offA[L];
+      const int dl = p.d[L], pl = p.pA[L], act = p.act[L - 1];
+      float part = 0.f;
+      for (int e = tid; e < nout; e += nthr) {
+        const int b = e / dl, n = e - b * dl;
+        const float a = AL[b * pl + n];
+        const float pred = p.has_map ? __fadd_rn(__fmul_rn(a, p.pa), p.pb) : a;
+        float val, grad;
+        mtd::loss_elem<KIND>(pred, sm[p.offT + e], p.scale, val, grad);
+        part += val;
+        if (p.has_map) grad = __fmul_rn(grad, p.pa);
+        if (act) grad = __fmul_rn(grad, __fsub_rn(1.f, __fmul_rn(a, a)));
+        AL[b * pl + n] = grad;
+      }
+      const float total = block_sum_rt(part, red);                 // ends with a barrier
+      if (tid == 0) S[p.offSL] = total;
+    }
+    // ---- backward, last layer first: partial dW into the scratch, G chain in place over the activations
+    for (int i = L - 1; i >= 0; --i) {
+      const float* G = sm + p.offA[i + 1];
+      float* Ain = sm + p.offA[i];
+      const float* Wi = sm + p.offW[i];
+      float* Sw = S + p.offSW[i];
+      const int dout = p.d[i + 1], din = p.d[i], pg = p.pA[i + 1], pa = p.pA[i], pw = p.pW[i];
+      // dW[n,k] = sum_b G[b,n] * Ain[b,k]   (zeros when this CTA has no rows)
+      run_gemm(p.dw[i], dout, din, B, G, 1, pg, Ain, pa, 1, [=](int n, int k, float v) { Sw[n * pw + k] = v; });
+      __syncthreads();
+      if (i > 0) {
+        // G_{i-1}[b,k] = (sum_n G[b,n] * W[n,k]) * tanh'(A_{i-1}[b,k]), over A_{i-1}
+        const int act = p.act[i - 1];
+        run_gemm(p.dx[i], B, din, dout, G, pg, 1, Wi, pw, 1, [=](int b, int k, float v) {
+          if (act) {
+            const float a = Ain[b * pa + k];
+            v = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(a, a)));
+          }
+          Ain[b * pa + k] = v;
+        });
+        __syncthreads();
+      }
+    }
+    // ---- exchange: every CTA folds the partials of all ranks in rank order and updates its weight replica
+    cluster_sync();
+    const bool last = (step == p.steps - 1);
+    for (int i = 0; i < L; ++i) {
+      float* Wi = sm + p.offW[i];
+      const float* Sw = S + p.offSW[i];
+      const int dout = p.d[i + 1], din = p.d[i], pw = p.pW[i];
+      float* gout = (last && rank == 0) ? p.gradW[i] : nullptr;
+      for (int e = tid; e < dout * din; e += nthr) {
+        const int n = e / din, k = e - n * din;
+        float gw = 0.f;
+        for (unsigned c = 0; c < csize; ++c) gw += ld_peer(Sw + n * pw + k, c);
+        Wi[n * pw + k] = __fsub_rn(Wi[n * pw + k], __fmul_rn(p.lr, gw));
+        if (gout) gout[e] = gw;
+      }
+    }
+    if (rank == 0 && tid == 0) {
+      float total = 0.f;
+      for (unsigned c = 0; c < csize; ++c) total += ld_peer(S + p.offSL, c);
+      p.losses[step] = __fmul_rn(total, p.scale);
+    }
+    __syncthreads();
+    // A_0 (= X rows) is never overwritten (no dX for the first layer); the other activations are rebuilt next step
+  }
+  cluster_sync();            // no CTA may exit while a peer can still read its shared memory
+  // ---- final weights (all replicas are identical)
+  if (rank == 0) {
+    for (int i = 0; i < L; ++i) {
+      const int dout = p.d[i + 1], din = p.d[i];
+      for (int e = tid; e < dout * din; e += nthr) {
+        const int n = e / din, k = e - n * din;
+        p.W[i][e] = sm[p.offW[i] + n * p.pW[i] + k];
+      }
+    }
+  }
+}
+
+inline int pow2_floor(int v) {
+  int r = 1;
+  while (r * 2 <= v) r *= 2;
+  return r;
+}
+
+Phase plan(int M, int N, int K, int nthreads) {
+  Phase ph;
+  const int i44 = (int)(ceil_div(M, 4) * ceil_div(N, 4)), i22 = (int)(ceil_div(M, 2) * ceil_div(N, 2));
+  int items;
+  if (i44 >= 128) { ph.tile = 0; items = i44; }
+  else if (i22 >= 128) { ph.tile = 1; items = i22; }
+  else { ph.tile = 2; items = M * N; }
+  int R = items >= nthreads ? 1 : pow2_floor(nthreads / std::max(items, 1));
+  R = std::min(R, 32);
+  R = std::min(R, pow2_floor(std::max(K, 1)));
+  ph.R = std::max(R, 1);
+  return ph;
+}
+
+inline int odd(int v) { return v | 1; }
+
+int g_mlp_cluster = 0;       // 0 = automatic cluster size, else forced (1, 2, 4, 8): mt_mlp_set_cluster
+
+}  // namespace
+
+MT_API int mt_mlp_fit_f32(const mt_mlp_desc* desc, const float* X, const float* T, int64_t batch, int loss_kind,
+                          int has_pred_map, float pred_scale, float pred_shift, float lr, float loss_scale, int steps,
+                          float* losses) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(desc && X && T && losses, "mt_mlp_fit_f32: null pointer");
+  MT_CHECK_ARG(desc->n_layers >= 1 && desc->n_layers <= MAXL, "mt_mlp_fit_f32: n_layers must be in [1, %d]", MAXL);
+  MT_CHECK_ARG(batch >= 1 && steps >= 0, "mt_mlp_fit_f32: batch >= 1 and steps >= 0 required");
+  MT_CHECK_ARG(loss_kind == MT_LOSS_MSE || loss_kind == MT_LOSS_CE_REF || loss_kind == MT_LOSS_BCE,
+               "mt_mlp_fit_f32: unknown loss kind %d", loss_kind);
+  if (steps == 0) return MT_OK;
+  if (batch > (1 << 20)) return fail(MT_ERR_UNSUPPORTED, "mt_mlp_fit_f32: batch does not fit on chip");
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.L = desc->n_layers;
+  p.B = (int)batch;
+  p.steps = steps;
+  p.loss_kind = loss_kind;
+  p.has_map = has_pred_map ? 1 : 0;
+  p.pa = pred_scale;
+  p.pb = pred_shift;
+  p.lr = lr;
+  p.scale = loss_scale;
+  p.X = X;
+  p.T = T;
+  p.losses = losses;
+  // cluster size: split the batch over up to 8 CTAs while every CTA keeps at least 8 rows
+  int csize = 1;
+  while (csize < 8 && batch / (csize * 2) >= 8) csize *= 2;
+  if (g_mlp_cluster > 0) csize = g_mlp_cluster;
+  p.rows_per = (int)ceil_div(batch, csize);
+  const int nthreads = csize > 1 ? 512 : THREADS;
+  size_t off = 0, sw = 0;
+  for (int i = 0; i <= p.L; ++i) {
+    MT_CHECK_ARG(desc->dims[i] >= 1 && desc->dims[i] <= 4096, "mt_mlp_fit_f32: dims[%d] = %d out of range", i, desc->dims[i]);
+    p.d[i] = desc->dims[i];
+    p.pA[i] = odd(p.d[i]);
+  }
+  for (int i = 0; i < p.L; ++i) {
+    MT_CHECK_ARG(desc->weight[i], "mt_mlp_fit_f32: weight[%d] is null", i);
+    p.W[i] = desc->weight[i];
+    p.bias[i] = desc->bias[i];
+    p.gradW[i] = desc->grad_weight[i];
+    p.act[i] = desc->act[i] == MT_ACT_TANH ? 1 : 0;
+    MT_CHECK_ARG(desc->act[i] == MT_ACT_NONE || desc->act[i] == MT_ACT_TANH, "mt_mlp_fit_f32: act[%d] unknown", i);
+    p.pW[i] = odd(p.d[i]);
+    p.offW[i] = (int)off;
+    off += (size_t)p.d[i + 1] * p.pW[i];
+    p.offSW[i] = (int)sw;
+    sw += (size_t)p.d[i + 1] * p.pW[i];
+    p.offB[i] = (int)off;
+    off += p.d[i + 1];
+    p.fwd[i] = plan(p.rows_per, p.d[i + 1], p.d[i], nthreads);
+    p.dw[i] = plan(p.d[i + 1], p.d[i], p.rows_per, nthreads);
+    p.dx[i] = plan(p.rows_per, p.d[i], p.d[i + 1], nthreads);
+  }
+  p.offSL = (int)sw;
+  sw += 1;
+  for (int i = 0; i <= p.L; ++i) {
+    p.offA[i] = (int)off;
+    off += (size_t)p.rows_per * p.pA[i];
+  }
+  p.offT = (int)off;
+  off += (size_t)p.rows_per * p.d[p.L];
+  p.offS[0] = (int)off;
+  p.offS[1] = (int)(off + sw);
+  off += 2 * sw;
+  const size_t bytes = off * sizeof(float);
+  if (bytes > (size_t)SMEM_MAX)
+    return fail(MT_ERR_UNSUPPORTED, "mt_mlp_fit_f32: model + batch need %zu bytes of shared memory per CTA (limit %d)", bytes,
+                SMEM_MAX);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(csize, 1, 1);
+  cfg.blockDim = dim3(nthreads, 1, 1);
+  cfg.dynamicSmemBytes = bytes;
+  cfg.stream = g().stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define MT_FIT(KIND)                                                                                              \
+  do {                                                                                                            \
+    auto kern = mlp_fit_kernel<KIND>;                                                                             \
+    static bool set = false;                                                                                      \
+    if (!set) { MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX)); set = true; } \
+    MT_CUDA(cudaLaunchKernelEx(&cfg, kern, p));                                                                   \
+  } while (0)
+  switch (loss_kind) {
+    case MT_LOSS_MSE: MT_FIT(MT_LOSS_MSE); break;
+    case MT_LOSS_CE_REF: MT_FIT(MT_LOSS_CE_REF); break;
+    default: MT_FIT(MT_LOSS_BCE); break;
+  }
+#undef MT_FIT
+  MT_LAUNCHED();
+  return MT_OK;
+}
+
+// tuning / test knob: force the cluster size of mt_mlp_fit_f32 (0 = automatic)
+extern "C" __attribute__((visibility("default"))) int mt_mlp_set_cluster(int csize) {
+  if (!(csize == 0 || csize == 1 || csize == 2 || csize == 4 || csize == 8))
+    return mt::fail(MT_ERR_INVALID, "mt_mlp_set_cluster: cluster size must be 0, 1, 2, 4 or 8");
+  g_mlp_cluster = csize;
+  return MT_OK;
+}

@@ -44,6 +44,101 @@ def train_step(model: Module, loss_fn: Loss, optimizer: SGD, x: Tensor, target: 
     return loss
 
 
+def _small_mlp_plan(model: Module, loss_fn: Loss, optimizer: SGD, x: Tensor, target: Tensor):
+    """(layers, acts) when `model` is a Sequential of Linear [+ Tanh] blocks of the kind the single-launch trainer
+    (mt_mlp_fit_f32) runs; None otherwise.  Pure host logic; whether model + batch fit on chip is the library's call."""
+    from .nn.activation import Tanh
+    from .nn.layer.linear import Linear
+    from .nn.sequential import Sequential
+    if type(model) is not Sequential or type(optimizer) is not SGD or loss_fn._kind is None or loss_fn.reduction != "mean":
+        return None
+    if getattr(loss_fn, "world", 1) != 1 or x.device != Device.CUDA or target.device != Device.CUDA or x.ndim != 2:
+        return None
+    layers, acts, mods, i = [], [], model.modules, 0
+    while i < len(mods):
+        if type(mods[i]) is not Linear:
+            return None
+        layers.append(mods[i])
+        if i + 1 < len(mods) and type(mods[i + 1]) is Tanh:
+            acts.append(_capi.ACT_TANH)
+            i += 2
+        else:
+            acts.append(_capi.ACT_NONE)
+            i += 1
+    if not 1 <= len(layers) <= _capi.MLP_MAX_LAYERS or layers[0].in_features != x.shape[1]:
+        return None
+    if any(a.out_features != b.in_features for a, b in zip(layers[:-1], layers[1:])):
+        return None
+    if target.size != x.shape[0] * layers[-1].out_features:
+        return None
+    return layers, acts
+
+
+def fit(model: Module, loss_fn: Loss, optimizer: SGD, x: Tensor, target: Tensor, steps: int,
+        pred_map: Optional[Tuple[float, float]] = None, squeeze_dim: Optional[int] = None,
+        fused: Optional[bool] = None) -> np.ndarray:
+    """`steps` iterations of the reference's full-batch loop (demo.ipynb:5178-5189) on fixed x / target;
+    returns the float32 loss of every step.
+
+    A small Linear(+Tanh) stack on CUDA runs as ONE kernel launch for the whole loop (mt_mlp_fit_f32: weights,
+    activations and gradients never leave the shared memory of a thread-block cluster); anything else runs `train_step` per iteration.  Both are
+    device paths.  `fused=True` insists on the single-launch kernel (ValueError if the model does not qualify),
+    `fused=False` forces the per-step path.  Afterwards parameters hold the trained weights and `.grad` the last
+    step's gradients, exactly as after the loop."""
+    plan = None if fused is False else _small_mlp_plan(model, loss_fn, optimizer, x, target)
+    if squeeze_dim is not None and plan is not None:
+        ok = x.shape[0] * plan[0][-1].out_features == target.size and plan[0][-1].out_features == 1
+        plan = plan if ok else None
+    if plan is None:
+        if fused:
+            raise ValueError("fit(fused=True): the model / loss / batch do not qualify for the single-launch trainer")
+        return np.array([train_step(model, loss_fn, optimizer, x, target, pred_map, squeeze_dim).item()
+                         for _ in range(steps)], dtype=np.float32)
+    import ctypes as C
+    from .cuda.array import DeviceArray
+    layers, acts = plan
+    for m in (model, *model.modules):                       # the first-call device migration (Q6)
+        if not getattr(m, "_device_initialized", False):
+            m.to(x.device)
+            m._device_initialized = True
+    desc = _capi.MlpDesc()
+    desc.n_layers = len(layers)
+    desc.dims[0] = layers[0].in_features
+    grads = []
+    for k, layer in enumerate(layers):
+        desc.dims[k + 1] = layer.out_features
+        desc.act[k] = acts[k]
+        wdata = layer.weight.data
+        if not wdata.is_dense:
+            raise ValueError("fit: weights must be dense arrays")
+        desc.weight[k] = wdata.ptr
+        desc.bias[k] = layer.bias.data.dense().ptr if layer.bias is not None else None
+        g = DeviceArray.empty(wdata.shape)
+        grads.append(g)
+        desc.grad_weight[k] = g.ptr
+    xd, td = x.data.dense(), target.data.dense()
+    losses = DeviceArray.empty((max(steps, 1),))
+    a, b = (float(pred_map[0]), float(pred_map[1])) if pred_map is not None else (1.0, 0.0)
+    scale = float(np.float32(target.size) ** -1)
+    status = _capi.lib().mt_mlp_fit_f32(C.byref(desc), xd.ptr, td.ptr, x.shape[0], loss_fn._kind,
+                                        1 if pred_map is not None else 0, a, b, float(optimizer.lr), scale,
+                                        int(steps), losses.ptr)
+    if status == _capi.ERR_UNSUPPORTED:                      # model + batch do not fit in the cluster's shared memory
+        if fused:
+            raise ValueError("fit(fused=True): " + _capi.lib().mt_last_error().decode(errors="replace"))
+        return np.array([train_step(model, loss_fn, optimizer, x, target, pred_map, squeeze_dim).item()
+                         for _ in range(steps)], dtype=np.float32)
+    _capi.check(status, "mt_mlp_fit_f32")
+    if steps > 0:
+        for layer, g in zip(layers, grads):
+            layer.weight.data._host_value = None
+            g._owned = True
+            layer.weight.grad = g
+            if layer.bias is not None:
+                layer.bias.zero_grad()                       # biases get no gradient in the reference (Q1)
+    return losses.get()[:steps].astype(np.float32)
+
+
 def shard_rows(n_rows: int, rank: int, world: int) -> slice:
     """Contiguous row shard [r*n/W, (r+1)*n/W) of a batch (the batch must divide evenly)."""
     if n_rows % world:

@@ -158,3 +158,25 @@ def test_checkpoint_round_trip_and_resume_cpu(tmp_path):
     junk.write_bytes(b"not a checkpoint")
     with pytest.raises(ValueError):
         ck.load_checkpoint(junk, fresh)
+
+
+def test_fit_on_cpu_is_the_per_step_loop():
+    """trainer.fit away from CUDA is the reference's loop verbatim (the single-launch kernel is CUDA-only and
+    `fused=True` refuses instead of falling back silently)."""
+    from microtorch_b200 import workloads as W
+    import microtorch_b200.nn as nn
+    from microtorch_b200.nn.activation import Tanh
+    from microtorch_b200.nn.loss import MSELoss
+    from microtorch_b200.nn.optimizer import SGD
+    from microtorch_b200.tensor import Tensor
+    from microtorch_b200.trainer import fit, train_step
+    wl = W.C1A
+    model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+    X, T = Tensor(x), Tensor(t)
+    got = fit(model, MSELoss(), SGD(model.parameters, lr=wl.lr), X, T, 5, wl.pred_map, wl.squeeze_dim)
+    model2, _, _ = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+    opt2, loss2 = SGD(model2.parameters, lr=wl.lr), MSELoss()
+    want = [train_step(model2, loss2, opt2, X, T, wl.pred_map, wl.squeeze_dim).item() for _ in range(5)]
+    np.testing.assert_array_equal(got, np.array(want, np.float32))
+    with pytest.raises(ValueError):
+        fit(model, MSELoss(), SGD(model.parameters, lr=wl.lr), X, T, 1, wl.pred_map, wl.squeeze_dim, fused=True)

@@ -4,6 +4,7 @@ the golden vectors made by running the reference.  Needs a B200: `-m gpu` under 
 The tests read like the reference's own (`Tensor(..., device="cuda")`, `.backward()`, `.to("cpu")`).
 Tolerances (north_star): index/shape ops bit-exact; elementwise + reductions 1e-5 relative;
 GEMM paths 1e-4 relative (norm-wise: |err| <= 1e-4 * max|ref|)."""
+import ctypes as C
 import json
 import os
 
@@ -689,3 +690,90 @@ def test_checkpoint_resume_on_cuda_is_bit_exact(mt, tmp_path):
     assert t1.device.value == "cuda" and t1.requires_grad
     np.testing.assert_array_equal(host(t1.data), host(t0.data))
     np.testing.assert_array_equal(host(t1.grad), host(t0.grad))
+
+
+def run_fit(mt, wl, steps, fused):
+    from microtorch_b200.trainer import fit
+    model, x, t = W.setup(wl, mt.Linear, mt.Tanh, mt.Sequential)
+    X, T = mt.Tensor(x, device="cuda"), mt.Tensor(t, device="cuda")
+    loss_fn, opt = mt.losses[wl.loss](), mt.SGD(model.parameters, lr=wl.lr)
+    mt.lib.mt_launch_count_reset()
+    losses = fit(model, loss_fn, opt, X, T, steps, wl.pred_map, wl.squeeze_dim, fused=fused)
+    n = C.c_uint64()
+    mt.lib.mt_launch_count(C.byref(n))
+    params = list(model.parameters())
+    return {"losses": losses, "params": [host(p.data) for p in params], "grads": [host(p.grad) for p in params],
+            "launches": n.value}
+
+
+def test_single_launch_trainer_reproduces_the_notebook_and_the_reference(mt):
+    """SURVEY.md section 8f item 1, taken to its end: the whole training loop of the spiral demo in ONE kernel launch
+    (mt_mlp_fit_f32).  Loss stream vs the notebook's published values (steps 0..100, 1e-5) and vs the reference
+    golden run (120 steps: losses, final weights, last-step gradients, constant biases)."""
+    pub = json.load(open(os.path.join(GOLDEN, "c1a_notebook_losses.json")))["losses"]
+    res = run_fit(mt, W.C1A, 120, fused=True)
+    assert res["launches"] == 1
+    want = np.array([float(pub[str(i)]) for i in range(101)], dtype=np.float32)
+    np.testing.assert_allclose(res["losses"][:101], want, rtol=1e-5)
+    g = load("c1a_ref_120steps")
+    np.testing.assert_allclose(res["losses"], g["losses"], rtol=1e-4)
+    for i, (gr, pr) in enumerate(zip(res["grads"], res["params"])):
+        gemm_close(pr, g[f"param{i}"], 1e-4 if i % 2 == 0 else 0.0)        # biases never move: exact
+        gemm_close(gr, g[f"grad{i}"], 2e-3)
+    assert not any(np.any(gr) for gr in res["grads"][1::2])                  # biases: zero gradient (Q1)
+
+
+@pytest.mark.parametrize("wl,steps", [
+    (W.C1B, 20),                                                              # 2 -> 100 -> 3, MSE on (200, 3) targets
+    (W.scaled(W.C2, 96, (48, 80, 64, 10)), 3),                                # CE with the 0.49*y+0.5 prediction map
+    (W.scaled(W.C5, 64, (32,) * 5), 2),                                       # 4 equal layers, MSE
+    (W.scaled(W.C2, 37, (5, 7, 3)), 4),                                       # ragged everything
+])
+def test_single_launch_trainer_equals_per_step_path(mt, wl, steps):
+    """Same model, same data: one launch for the loop vs one fused-kernel sequence per step (itself checked against
+    the reference goldens).  Different summation orders, so 1e-5 on the losses and 1e-4 norm-wise on weights/grads."""
+    one = run_fit(mt, wl, steps, fused=True)
+    per = run_fit(mt, wl, steps, fused=False)
+    assert one["launches"] == 1 and per["launches"] > steps
+    np.testing.assert_allclose(one["losses"], per["losses"], rtol=1e-5)
+    for a, b in zip(one["params"], per["params"]):
+        gemm_close(a, b, 1e-4)
+    for a, b in zip(one["grads"], per["grads"]):
+        gemm_close(a, b, 1e-4)
+
+
+def test_single_launch_trainer_declines_what_does_not_fit(mt):
+    from microtorch_b200.trainer import fit
+    wl = W.scaled(W.C2, 4096, (1024, 512, 10))
+    model, x, t = W.setup(wl, mt.Linear, mt.Tanh, mt.Sequential)
+    X, T = mt.Tensor(x, device="cuda"), mt.Tensor(t, device="cuda")
+    loss_fn, opt = mt.losses[wl.loss](), mt.SGD(model.parameters, lr=wl.lr)
+    with pytest.raises(ValueError):
+        fit(model, loss_fn, opt, X, T, 1, wl.pred_map, wl.squeeze_dim, fused=True)
+    losses = fit(model, loss_fn, opt, X, T, 2, wl.pred_map, wl.squeeze_dim)   # auto: per-step device path
+    assert losses.shape == (2,) and np.isfinite(losses).all()
+
+
+@pytest.mark.parametrize("csize", [1, 2, 4, 8])
+def test_single_launch_trainer_cluster_sizes_agree(mt, csize):
+    """The batch split over 1/2/4/8 CTAs of a cluster (partial dW exchanged through DSMEM) trains the same model:
+    only the summation order over rows changes."""
+    mt.lib.mt_mlp_set_cluster.argtypes = [C.c_int]
+    try:
+        assert mt.lib.mt_mlp_set_cluster(csize) == 0
+        got = run_fit(mt, W.C1A, 60, fused=True)
+    finally:
+        mt.lib.mt_mlp_set_cluster(0)
+    g = load("c1a_ref_120steps")
+    np.testing.assert_allclose(got["losses"], g["losses"][:60], rtol=2e-5)
+    assert got["launches"] == 1
+    ragged = W.scaled(W.C2, 37, (5, 7, 3))               # 37 rows over 8 CTAs: the last ranks own 2 rows or none
+    try:
+        mt.lib.mt_mlp_set_cluster(csize)
+        a = run_fit(mt, ragged, 4, fused=True)
+    finally:
+        mt.lib.mt_mlp_set_cluster(0)
+    b = run_fit(mt, ragged, 4, fused=False)
+    np.testing.assert_allclose(a["losses"], b["losses"], rtol=1e-5)
+    for x, y in zip(a["params"], b["params"]):
+        gemm_close(x, y, 1e-4)

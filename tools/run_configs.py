@@ -94,13 +94,33 @@ def main():
                           "last_loss": g.result.item()}), flush=True)
         g.close()
 
+    def run_single_launch(wl, steps, tag):
+        from microtorch_b200.trainer import fit
+        model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+        X, T = Tensor(x, device="cuda"), Tensor(t, device="cuda")
+        loss_fn, opt = losses[wl.loss](), SGD(model.parameters, lr=wl.lr)
+        fit(model, loss_fn, opt, X, T, 50, wl.pred_map, wl.squeeze_dim, fused=True)       # warm-up (module load, migration)
+        lib.mt_sync()
+        lib.mt_event_record(e0)
+        ls = fit(model, loss_fn, opt, X, T, steps, wl.pred_map, wl.squeeze_dim, fused=True)
+        lib.mt_event_record(e1)
+        lib.mt_event_sync(e1)
+        ms = C.c_float()
+        lib.mt_event_elapsed_ms(e0, e1, C.byref(ms))
+        print(json.dumps({"config": tag + "_single_launch_loop", "steps": steps, "ms_per_step": ms.value / steps,
+                          "us_per_step": 1e3 * ms.value / steps, "steps_per_s": steps / (ms.value / 1e3),
+                          "samples_per_s": wl.batch * steps / (ms.value / 1e3), "launches": 1,
+                          "last_loss": float(ls[-1])}), flush=True)
+
     want = lambda k: (not args.only) or k in args.only.split(",")
     if want("c1a"):
         run(W.C1A, 2000, 50, "c1a_spiral_notebook_mlp_2_64_32_16_1")
         run_graphed(W.C1A, 5000, "c1a_spiral_notebook_mlp_2_64_32_16_1")
+        run_single_launch(W.C1A, 5000, "c1a_spiral_notebook_mlp_2_64_32_16_1")
     if want("c1b"):
         run(W.C1B, 2000, 50, "c1b_spiral_2_100_3")
         run_graphed(W.C1B, 5000, "c1b_spiral_2_100_3")
+        run_single_launch(W.C1B, 5000, "c1b_spiral_2_100_3")
     if want("c4"):
         k = args.c4_layers
         wl = W.Workload("c4", (2048,) * (k + 1), "bce", 0.01, 256, pred_map=(0.49, 0.5), seed=0, input_shape=(256, 512, 2048))

@@ -286,6 +286,34 @@ def test_tcgen05_engine_is_used_and_accurate(lib):
     assert gemm_err(dX.get(), dz @ W) < 1e-5
 
 
+RAGGED = [(1000, 260, 100), (129, 68, 4100), (131, 516, 1028), (2049, 257, 260), (128, 64, 2052), (257, 4100, 36),
+          (4099, 132, 132), (640, 1100, 516), (128, 4096, 8196), (8200, 200, 64)]
+
+
+@pytest.mark.parametrize("M,N,K", RAGGED)
+def test_linear_ragged_shapes_on_tensor_cores(lib, M, N, K):
+    """Tile-ragged extents (M, N not multiples of 128/256, K not a multiple of 32, split-K and paired-CTA shapes) through
+    the tcgen05 path - forward with bias+tanh, dW with accumulation, dX with the producer's tanh' epilogue - vs float64."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    X = np.tanh(rng.standard_normal((M, K))).astype(np.float32)
+    W = (rng.standard_normal((N, K)) * (1.0 / np.sqrt(K))).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    dY = rng.standard_normal((M, N)).astype(np.float32)
+    Xd, Wd, bd, dYd, Y = Dev(X), Dev(W), Dev(b), Dev(dY), Dev(shape=(M, N))
+    eng = C.c_int(-5)
+    _capi.check(lib.mt_linear_fwd_f32(Y.ptr, Xd.ptr, Wd.ptr, bd.ptr, M, N, K, 1))
+    lib.mt_gemm_last_engine(C.byref(eng))
+    # the tensor-core path stores 128-bit rows: N % 4 != 0 is served by the SIMT tile (still checked below)
+    assert eng.value == (1 if N % 4 == 0 else 0), "unexpected GEMM engine for this shape"
+    Yh = Y.get()
+    assert gemm_err(Yh, np.tanh(X.astype(np.float64) @ W.astype(np.float64).T + b)) < 2e-5
+    dX, dW = Dev(shape=(M, K)), Dev(np.full((N, K), 0.5, np.float32))
+    _capi.check(lib.mt_linear_bwd_f32(dX.ptr, dW.ptr, dYd.ptr, Y.ptr, Xd.ptr, Wd.ptr, M, N, K, 1 | 2))
+    dz = dY.astype(np.float64) * (1 - Yh.astype(np.float64) ** 2)
+    assert gemm_err(dW.get(), dz.T @ X + 0.5) < 2e-5
+    assert gemm_err(dX.get(), (dz @ W) * (1 - X.astype(np.float64) ** 2)) < 2e-5
+
+
 def test_matmul_generic_strided_and_batched(lib):
     rng = np.random.default_rng(11)
     A = rng.standard_normal((4, 33, 20)).astype(np.float32)

@@ -99,6 +99,10 @@ def main():
         model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
         X, T = Tensor(x, device="cuda"), Tensor(t, device="cuda")
         loss_fn, opt = losses[wl.loss](), SGD(model.parameters, lr=wl.lr)
+        if os.environ.get("MT_MLP_THREADS"):                 # tuning knobs of the on-chip trainer
+            _capi.check(lib.mt_mlp_set_threads(int(os.environ["MT_MLP_THREADS"])))
+        if os.environ.get("MT_MLP_CLUSTER"):
+            _capi.check(lib.mt_mlp_set_cluster(int(os.environ["MT_MLP_CLUSTER"])))
         fit(model, loss_fn, opt, X, T, 50, wl.pred_map, wl.squeeze_dim, fused=True)       # warm-up (module load, migration)
         lib.mt_sync()
         lib.mt_event_record(e0)
@@ -107,12 +111,20 @@ def main():
         lib.mt_event_sync(e1)
         ms = C.c_float()
         lib.mt_event_elapsed_ms(e0, e1, C.byref(ms))
-        print(json.dumps({"config": tag + "_single_launch_loop", "steps": steps, "ms_per_step": ms.value / steps,
+        clk = (C.c_ulonglong * 8)()
+        lib.mt_mlp_debug_clocks(1, clk)                     # phase clocks of rank 0 for a second, instrumented run
+        fit(model, loss_fn, opt, X, T, steps, wl.pred_map, wl.squeeze_dim, fused=True)
+        lib.mt_mlp_debug_clocks(0, clk)
+        phases = dict(zip(["fwd", "loss", "dx", "dw", "cluster_barrier", "exchange_update"], [c / steps for c in clk[:6]]))
+        print(json.dumps({"config": tag + "_single_launch_loop", "steps": steps, "sm_cycles_per_step_by_phase": phases, "ms_per_step": ms.value / steps,
                           "us_per_step": 1e3 * ms.value / steps, "steps_per_s": steps / (ms.value / 1e3),
                           "samples_per_s": wl.batch * steps / (ms.value / 1e3), "launches": 1,
                           "last_loss": float(ls[-1])}), flush=True)
 
-    want = lambda k: (not args.only) or k in args.only.split(",")
+    want = lambda k: (not args.only and k != "c1fit") or k in args.only.split(",")
+    if want("c1fit"):
+        run_single_launch(W.C1A, 5000, "c1a_spiral_notebook_mlp_2_64_32_16_1")
+        run_single_launch(W.C1B, 5000, "c1b_spiral_2_100_3")
     if want("c1a"):
         run(W.C1A, 2000, 50, "c1a_spiral_notebook_mlp_2_64_32_16_1")
         run_graphed(W.C1A, 5000, "c1a_spiral_notebook_mlp_2_64_32_16_1")

@@ -138,6 +138,40 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(float* __restrict_
   }
 }
 
+// few splits (the tcgen05 split-K: S <= 8): fold the stacked partials and run the epilogue in ONE pass, split order
+// 0..S-1 (deterministic).  Traffic 4*M*N*(S+1) instead of 4*M*N*(S+3) for reduce + epilogue.
+__global__ void __launch_bounds__(256) splitk_fold_kernel(float* __restrict__ C, const float* __restrict__ partial, int splits,
+                                                          const float* __restrict__ bias, long long M, long long N, int act,
+                                                          int accumulate, const float* __restrict__ epi_tanh) {
+  const long long total4 = (M * N) >> 2;             // N % 4 == 0 and 16-byte aligned bases (checked by the caller)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long plane = M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+    float4 v = mtd::ld_stream4(partial + 4 * i);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 u = mtd::ld_stream4(partial + sp * plane + 4 * i);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + (4 * i) % N));
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (act == MT_ACT_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+    if (epi_tanh) {
+      const float4 t = mtd::ld_stream4(epi_tanh + 4 * i);
+      v.x = __fmul_rn(v.x, __fsub_rn(1.f, __fmul_rn(t.x, t.x)));
+      v.y = __fmul_rn(v.y, __fsub_rn(1.f, __fmul_rn(t.y, t.y)));
+      v.z = __fmul_rn(v.z, __fsub_rn(1.f, __fmul_rn(t.z, t.z)));
+      v.w = __fmul_rn(v.w, __fsub_rn(1.f, __fmul_rn(t.w, t.w)));
+    }
+    if (accumulate) {
+      const float4 c = *reinterpret_cast<const float4*>(C + 4 * i);
+      v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+    }
+    mtd::st4(C + 4 * i, v);
+  }
+}
+
 template <int BM, int BN, int TM, int TN>
 int launch(const GemmArgs& a, long long batch) {
   dim3 grid((unsigned)ceil_div(a.N, BN), (unsigned)ceil_div(a.M, BM), (unsigned)(a.splits > 1 ? a.splits : batch));
@@ -154,6 +188,13 @@ static int g_skinny = 1;   // test hook: 0 routes tiny-N shapes through the gene
 
 int splitk_finalize(float* C, const float* partial, int splits, long long M, long long N, const float* bias, int act,
                     int accumulate, const float* epi_tanh) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (splits <= 16 && N % 4 == 0 && al16(C) && al16(partial) && (!bias || al16(bias)) && (!epi_tanh || al16(epi_tanh))) {
+    splitk_fold_kernel<<<ew_grid((M * N) >> 2, 256), 256, 0, g().stream>>>(C, partial, splits, bias, M, N, act, accumulate,
+                                                                          epi_tanh);
+    MT_LAUNCHED();
+    return MT_OK;
+  }
   float* sum = nullptr;
   int rc = pool_alloc((void**)&sum, sizeof(float) * (size_t)M * N);
   if (rc) return rc;

@@ -44,3 +44,21 @@ def test_no_gpu_means_loud_failure_not_fallback(lib):
     assert lib.mt_init(0) != 0
     with pytest.raises(_capi.MicrotorchB200Error):
         _capi.require_device(0)
+
+
+def test_header_is_plain_c_and_the_desc_struct_matches_ctypes(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++, no torch types), and the one struct it passes
+    by pointer must have the layout the ctypes mirror assumes."""
+    import subprocess
+    hdr = os.path.join(REPO, "include", "microtorch_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "microtorch_b200.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(mt_mlp_desc), offsetof(mt_mlp_desc, dims),'
+                   ' offsetof(mt_mlp_desc, act), offsetof(mt_mlp_desc, weight), offsetof(mt_mlp_desc, bias),'
+                   ' offsetof(mt_mlp_desc, grad_weight)); return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(REPO, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    D = _capi.MlpDesc
+    assert got == [C.sizeof(D), D.dims.offset, D.act.offset, D.weight.offset, D.bias.offset, D.grad_weight.offset]

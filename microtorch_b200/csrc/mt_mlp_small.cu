@@ -382,6 +382,10 @@ inline int pow2_floor(int v) {
   return r;
 }
 
+// Pick tile shape and reduction split for one product.  Measured on the notebook model: the phases are LATENCY bound
+// (a cost model that minimised shared-memory load + shuffle instructions - larger tiles, fewer lanes - ran 1.5x slower),
+// so the rule is: the largest tile that still yields >= 128 work items, then split the reduction over as many lanes as
+// it takes to occupy the CTA.
 int plan(Phase* out, int M, int N, int K, int nthreads) {
   Phase ph;
   M = std::max(M, 1);

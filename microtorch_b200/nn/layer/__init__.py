@@ -1,3 +1,5 @@
+"""Layers with parameters."""
+
 from .linear import Linear
 
-__all__ = ["Linear"]
+__all__ = ("Linear",)

@@ -1,10 +1,11 @@
 """Module base class (interface of the reference's src/nn/module.py): first-call device
-migration, train/eval flags, parameter enumeration in attribute order, zero_grad, to()."""
+migration, train/eval flags, parameter enumeration in attribute order, zero_grad, to() - plus what the
+reference lacks for resuming a run: named parameters and a state dict (see checkpoint.py)."""
 
 from __future__ import annotations
 
 from functools import wraps
-from typing import Any, Iterator
+from typing import Any, Dict, Iterator, Tuple
 
 from ..tensor import Tensor
 from ..tensor.device import Device
@@ -70,3 +71,19 @@ class Module:
             elif isinstance(value, Module):
                 value.to(device)
         return self
+
+    # ------------------------------------------------------------------ names / persistence (not in the reference)
+    def named_parameters(self) -> Iterator[Tuple[str, Parameter]]:
+        """(attribute path, Parameter) in the order of `parameters()`, e.g. "modules.0.weight"."""
+        from ..checkpoint import named_parameters
+        return named_parameters(self)
+
+    def state_dict(self) -> Dict[str, Any]:
+        """Host copies of every parameter by name."""
+        from ..checkpoint import state_dict
+        return state_dict(self)
+
+    def load_state_dict(self, state: Dict[str, Any], strict: bool = True) -> None:
+        """Write `state` into the existing parameter buffers (host or device) in place."""
+        from ..checkpoint import load_state_dict
+        load_state_dict(self, state, strict=strict)

@@ -1,7 +1,9 @@
-from .base import BaseOps
-from .elementwise import Elementwise
-from .math import MathOps
-from .overload import OverloadOps
-from .reduce import Reduce
+"""Autograd op families behind `Tensor` (device-agnostic: each op asks `backend_for(device)` for its kernels)."""
 
-__all__ = ["BaseOps", "Elementwise", "MathOps", "OverloadOps", "Reduce"]
+from .reduce import Reduce
+from .overload import OverloadOps
+from .math import MathOps
+from .elementwise import Elementwise
+from .base import BaseOps
+
+__all__ = ("BaseOps", "Elementwise", "MathOps", "OverloadOps", "Reduce")

@@ -180,3 +180,21 @@ def test_fit_on_cpu_is_the_per_step_loop():
     np.testing.assert_array_equal(got, np.array(want, np.float32))
     with pytest.raises(ValueError):
         fit(model, MSELoss(), SGD(model.parameters, lr=wl.lr), X, T, 1, wl.pred_map, wl.squeeze_dim, fused=True)
+
+
+def test_relu_sigmoid_activations_cpu():
+    """ReLU / Sigmoid (not in the reference) composed from Tensor ops: values and gradients vs closed forms."""
+    from microtorch_b200.nn.activation import ReLU, Sigmoid
+    from microtorch_b200.tensor import Tensor
+    xv = np.random.default_rng(3).standard_normal((7, 5)).astype(np.float32)
+    x = Tensor(xv, requires_grad=True)
+    r = ReLU()(x)
+    np.testing.assert_array_equal(r.data, np.maximum(xv, 0))
+    r.sum().backward()
+    np.testing.assert_array_equal(x.grad, (xv > 0).astype(np.float32))
+    x = Tensor(xv, requires_grad=True)
+    s = Sigmoid()(x)
+    want = 1.0 / (1.0 + np.exp(-xv.astype(np.float64)))
+    np.testing.assert_allclose(s.data, want, rtol=1e-6)
+    s.sum().backward()
+    np.testing.assert_allclose(x.grad, want * (1 - want), rtol=1e-5)

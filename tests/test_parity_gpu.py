@@ -777,3 +777,21 @@ def test_single_launch_trainer_cluster_sizes_agree(mt, csize):
     np.testing.assert_allclose(a["losses"], b["losses"], rtol=1e-5)
     for x, y in zip(a["params"], b["params"]):
         gemm_close(x, y, 1e-4)
+
+
+def test_relu_sigmoid_on_cuda_match_cpu_path(mt):
+    from microtorch_b200.nn.activation import ReLU, Sigmoid
+    xv = np.random.default_rng(35).standard_normal((65, 33)).astype(np.float32)
+    for act, exact in ((ReLU(), True), (Sigmoid(), False)):
+        res = []
+        for dev in ("cpu", "cuda"):
+            x = mt.Tensor(xv, requires_grad=True, device=dev)
+            y = act(x)
+            (y * y).sum().backward()
+            res.append((host(y.data), host(x.grad)))
+        if exact:
+            np.testing.assert_array_equal(res[0][0], res[1][0])
+            np.testing.assert_array_equal(res[0][1], res[1][1])
+        else:
+            np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-5)
+            np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-5, atol=1e-7)

@@ -73,6 +73,19 @@ int fail(int status, const char* fmt, ...);
 int pool_alloc(void** p, size_t bytes);
 int pool_free(void* p);
 
+// Scratch block from the pool, returned on every exit path (pool_free is stream-ordered, so handing the block back
+// right after the kernels that use it were queued is safe).
+struct PoolScratch {
+  void* ptr = nullptr;
+  PoolScratch() = default;
+  PoolScratch(const PoolScratch&) = delete;
+  PoolScratch& operator=(const PoolScratch&) = delete;
+  ~PoolScratch() { release(); }
+  int alloc(size_t bytes) { release(); return pool_alloc(&ptr, bytes); }
+  void release() { if (ptr) { pool_free(ptr); ptr = nullptr; } }
+  float* f32() const { return static_cast<float*>(ptr); }
+};
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // grid for a grid-stride elementwise kernel over `work` items with `per_block` items per block

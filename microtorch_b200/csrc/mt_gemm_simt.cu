@@ -195,14 +195,13 @@ int splitk_finalize(float* C, const float* partial, int splits, long long M, lon
     MT_LAUNCHED();
     return MT_OK;
   }
-  float* sum = nullptr;
-  int rc = pool_alloc((void**)&sum, sizeof(float) * (size_t)M * N);
+  PoolScratch sum;
+  int rc = sum.alloc(sizeof(float) * (size_t)M * N);
   if (rc) return rc;
-  rc = mt_reduce_sum_f32(sum, partial, 1, splits, M * N, nullptr, 0, 0, 0);
+  rc = mt_reduce_sum_f32(sum.f32(), partial, 1, splits, M * N, nullptr, 0, 0, 0);
   if (rc) return rc;
-  splitk_epilogue_kernel<<<ew_grid(M * N, 1024), 256, 0, g().stream>>>(C, sum, bias, M, N, act, accumulate, epi_tanh);
+  splitk_epilogue_kernel<<<ew_grid(M * N, 1024), 256, 0, g().stream>>>(C, sum.f32(), bias, M, N, act, accumulate, epi_tanh);
   MT_LAUNCHED();
-  pool_free(sum);
   return MT_OK;
 }
 
@@ -232,11 +231,11 @@ int gemm_simt(GemmArgs a, long long batch) {
   a.splits = (int)splits;
   a.kchunk = kchunk;
   float* final_c = a.C;
-  float* partial = nullptr;
+  PoolScratch partial;
   if (splits > 1) {
-    int rc = pool_alloc((void**)&partial, sizeof(float) * splits * a.M * a.N);
+    int rc = partial.alloc(sizeof(float) * splits * a.M * a.N);
     if (rc) return rc;
-    a.C = partial;
+    a.C = partial.f32();
   }
   int rc;
   if (shape == 0) rc = launch<128, 128, 8, 8>(a, batch);
@@ -244,8 +243,7 @@ int gemm_simt(GemmArgs a, long long batch) {
   else rc = launch<16, 256, 4, 4>(a, batch);
   if (rc) return rc;
   if (splits > 1) {
-    rc = splitk_finalize(final_c, partial, (int)splits, a.M, a.N, a.bias, a.act, a.accumulate, a.epi_tanh);
-    pool_free(partial);
+    rc = splitk_finalize(final_c, partial.f32(), (int)splits, a.M, a.N, a.bias, a.act, a.accumulate, a.epi_tanh);
     if (rc) return rc;
   }
   return MT_OK;

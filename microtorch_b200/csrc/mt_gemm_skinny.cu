@@ -351,9 +351,10 @@ int run_dw(const GemmArgs& a, long long ldz, long long ldx) {
   long long ctas = std::min<long long>((long long)g().sm_count, ceil_div(rows, 256));
   const long long slab = ceil_div(ceil_div(rows, ctas), DZ_ROWS) * DZ_ROWS;
   ctas = ceil_div(rows, slab);
-  float* partial = nullptr;
-  int rc = pool_alloc((void**)&partial, sizeof(float) * (size_t)ctas * a.M * Kc);
+  PoolScratch scratch;
+  int rc = scratch.alloc(sizeof(float) * (size_t)ctas * a.M * Kc);
   if (rc) return rc;
+  float* partial = scratch.f32();
   if (g_skinny_ring) {
 #define MT_DWR(CGV)                                                                                                    \
   do {                                                                                                                 \
@@ -381,9 +382,7 @@ int run_dw(const GemmArgs& a, long long ldz, long long ldx) {
 #undef MT_DW
   }
   MT_LAUNCHED();
-  rc = splitk_finalize(a.C, partial, (int)ctas, a.M, Kc, nullptr, MT_ACT_NONE, a.accumulate, nullptr);
-  pool_free(partial);
-  return rc;
+  return splitk_finalize(a.C, partial, (int)ctas, a.M, Kc, nullptr, MT_ACT_NONE, a.accumulate, nullptr);
 }
 
 template <typename F4, typename F8, typename F12, typename F16>

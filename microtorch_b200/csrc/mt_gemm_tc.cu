@@ -748,10 +748,12 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   }
   p.kb_per_split = (int)ceil_div(p.k_blocks, S);
   p.splits = (int)ceil_div(p.k_blocks, p.kb_per_split);
+  PoolScratch scratch;
   float* partial = nullptr;
   if (p.splits > 1) {
-    rc = pool_alloc((void**)&partial, sizeof(float) * (size_t)p.splits * a.M * a.N);
+    rc = scratch.alloc(sizeof(float) * (size_t)p.splits * a.M * a.N);
     if (rc) return rc;
+    partial = scratch.f32();
     p.C = partial;
     p.bias = nullptr;
     p.epi_tanh = nullptr;
@@ -796,7 +798,6 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   MT_LAUNCHED();
   if (partial) {
     rc = splitk_finalize(a.C, partial, p.splits, a.M, a.N, a.bias, a.act, a.accumulate, a.epi_tanh);
-    pool_free(partial);
     if (rc) return rc;
   }
   return MT_OK;

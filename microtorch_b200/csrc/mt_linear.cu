@@ -69,11 +69,13 @@ MT_API int mt_linear_bwd_f32(float* dX, float* dW, const float* dY, const float*
   if (N == 0 || K == 0) return MT_OK;
   int engine = 1;
   const float* dZ = dY;          // explicit dZ, materialised only if an engine needs it
+  PoolScratch dz_scratch;
   float* dZ_tmp = nullptr;
   auto need_explicit = [&]() -> int {
     if (!Yact || dZ_tmp) return MT_OK;
-    int rc = pool_alloc((void**)&dZ_tmp, sizeof(float) * (size_t)M * N);
+    int rc = dz_scratch.alloc(sizeof(float) * (size_t)M * N);
     if (rc) return rc;
+    dZ_tmp = dz_scratch.f32();
     const int64_t shape[1] = {M * N}, st[1] = {1};
     rc = mt_ew_binary_f32(MT_BIN_TANH_BWD, dZ_tmp, dY, Yact, 1, shape, st, st, 0.f);
     dZ = dZ_tmp;
@@ -124,7 +126,6 @@ MT_API int mt_linear_bwd_f32(float* dX, float* dW, const float* dY, const float*
     if (dx_preact) a.epi_tanh = X;   // X is the tanh output of the producing layer: emit ITS dZ directly
     rc = attempt(a);
   }
-  if (dZ_tmp) pool_free(dZ_tmp);
   g().gemm_last_engine = engine;
   return rc;
 }

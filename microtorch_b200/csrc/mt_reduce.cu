@@ -183,10 +183,12 @@ int reduce_rows(float* out, const float* x, long long outer, long long red, cons
   splits = ceil_div(red, chunk);
   const bool vec = aligned16(x) && red % 4 == 0 && (!w || (aligned16(w) && sr == 1 && so % 4 == 0));
   float* dst = out;
+  PoolScratch scratch;
   float* partial = nullptr;
   if (splits > 1) {
-    int rc = pool_alloc((void**)&partial, sizeof(float) * outer * splits);
+    int rc = scratch.alloc(sizeof(float) * outer * splits);
     if (rc) return rc;
+    partial = scratch.f32();
     dst = partial;
   }
   const int grid = (int)std::min<long long>(outer * splits, (long long)sms * 8);
@@ -197,7 +199,6 @@ int reduce_rows(float* out, const float* x, long long outer, long long red, cons
   MT_LAUNCHED();
   if (splits > 1) {
     int rc = reduce_rows(out, partial, outer, splits, nullptr, 0, 0);
-    pool_free(partial);  // stream-ordered: the second pass was queued before any reuse
     return rc;
   }
   return MT_OK;
@@ -220,10 +221,12 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
   const long long chunk = ceil_div(red, splits);
   splits = ceil_div(red, chunk);
   float* dst = out;
+  PoolScratch scratch;
   float* partial = nullptr;
   if (splits > 1) {
-    int rc = pool_alloc((void**)&partial, sizeof(float) * outer * splits * inner);
+    int rc = scratch.alloc(sizeof(float) * outer * splits * inner);
     if (rc) return rc;
+    partial = scratch.f32();
     dst = partial;
   }
   dim3 grid((unsigned)tiles, (unsigned)splits, (unsigned)oz);
@@ -234,7 +237,6 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
   MT_LAUNCHED();
   if (splits > 1) {
     int rc = reduce_cols(out, partial, outer, splits, inner, nullptr, 0, 0, 0);
-    pool_free(partial);
     return rc;
   }
   return MT_OK;
@@ -325,10 +327,12 @@ int reduce_extreme(float* out, const float* x, long long outer, long long red, l
   chunk = (chunk + 3) & ~3LL;
   splits = ceil_div(red, chunk);
   float* dst = out;
+  PoolScratch scratch;
   float* partial = nullptr;
   if (splits > 1) {
-    int rc = pool_alloc((void**)&partial, sizeof(float) * outer * splits * inner);
+    int rc = scratch.alloc(sizeof(float) * outer * splits * inner);
     if (rc) return rc;
+    partial = scratch.f32();
     dst = partial;
   }
   if (inner == 1) {
@@ -341,7 +345,6 @@ int reduce_extreme(float* out, const float* x, long long outer, long long red, l
   MT_LAUNCHED();
   if (splits > 1) {
     int rc = reduce_extreme<IS_MAX>(out, partial, outer, splits, inner);
-    pool_free(partial);  // stream-ordered
     return rc;
   }
   return MT_OK;

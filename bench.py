@@ -140,7 +140,7 @@ def cpu_baseline(steps=3, warmup=1):
                       "NumPy elementwise is single-threaded, only matmul uses all cores"}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference
     is pure Python and cannot travel to the GPU box), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -165,7 +165,7 @@ def run_reference(args):
     except Exception:
         cores = os.cpu_count()
     sample = f"config #2 model, batch {CPU_SAMPLE_BATCH} per step (bounded sample of 65536)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "mlp_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -173,7 +173,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": int(cores), "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}), flush=True)
+        "gpu_launches": 0})
 
 
 def main():
@@ -186,8 +186,18 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="rows per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line - the JSON result.  Libraries write banners to fd 1 (NCCL prints its version
+    # there when NCCL_DEBUG asks for it), so everything else is sent to stderr for the duration of the run.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, emit)
     args.warmup = max(args.warmup, 3)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -351,7 +361,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(out), flush=True)
+    emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -795,3 +795,12 @@ def test_relu_sigmoid_on_cuda_match_cpu_path(mt):
         else:
             np.testing.assert_allclose(res[1][0], res[0][0], rtol=1e-5)
             np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-5, atol=1e-7)
+
+
+def test_full_size_step_against_the_oracle(mt):
+    """BASELINE config #2 at its full size (B = 65536 when the host has the memory): one training step on the device vs
+    the oracle on the host cores - loss, every weight gradient, every updated weight within 1e-4 (measured 2e-7 / 5e-6 /
+    7e-8, profiles/r01_c2_full_size_parity.json); biases bit-identical."""
+    import full_size_parity
+    rec = full_size_parity.run()
+    assert rec["pass"], rec

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--step", type=int, default=2)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--graph", action="store_true", help="also time CUDA-graph replays of the tape workloads")
+    ap.add_argument("--graph-max", type=int, default=24, help="largest log2(N) to capture as a graph")
     args = ap.parse_args()
     from microtorch_b200 import _capi
     _capi.require_device(0)
@@ -64,6 +66,7 @@ def main():
               "col": rng.uniform(0.5, 1.5, (R, 1)).astype(np.float32), "scalar": np.float32(1.25).reshape(())}
         B = 4.0 * n
         work = {}
+        graphs = []
         for tag, yh in ys.items():
             y = Tensor(yh, requires_grad=True, device="cuda")
             m = 4.0 * yh.size
@@ -113,6 +116,14 @@ def main():
             xp.zero_grad()
             lossf(xp, yt).backward()
         work["mse_loss_fwd_bwd"] = (f_loss, 3 * B)
+        # launch-bound sizes: the same workload captured once and replayed as ONE CUDA graph (graph.GraphedStep)
+        if args.graph and p <= args.graph_max:
+            from microtorch_b200.graph import GraphedStep
+            for name in [k for k in list(work) if k.startswith(("poly_", "log_", "tanh_", "mean_", "mse_"))]:
+                fn, nbytes = work[name]
+                gs = GraphedStep(fn, warmup=2)
+                graphs.append(gs)
+                work[name + "_cuda_graph"] = (gs.replay, nbytes)
         for name, (fn, nbytes) in work.items():
             if args.only and not any(k in name for k in args.only.split(',')):
                 continue
@@ -120,6 +131,8 @@ def main():
             rec = {"workload": name, "log2_n": p, "ms": ms, "alg_gb": nbytes / 1e9, "gbs": nbytes / ms / 1e6,
                    "frac_of_measured_hbm": nbytes / ms / 1e6 / peak}
             print(json.dumps(rec), flush=True)
+        for gs in graphs:
+            gs.close()
         del x, work
 
 

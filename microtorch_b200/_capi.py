@@ -8,6 +8,7 @@ CUDA path never silently runs somewhere else.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 from typing import Optional, Sequence
 
@@ -175,5 +176,12 @@ def device_ready() -> bool:
     return _DEVICE_READY
 
 
-def i64(values: Sequence[int]):
+@functools.lru_cache(maxsize=8192)
+def _i64_tuple(values: tuple):
     return (C.c_int64 * max(len(values), 1))(*values)
+
+
+def i64(values: Sequence[int]):
+    """int64[] argument for shapes / strides.  The arrays are read-only on both sides of the ABI, so one ctypes array
+    per distinct tuple is built once and shared (this call sits on the per-launch host path)."""
+    return _i64_tuple(values if type(values) is tuple else tuple(values))

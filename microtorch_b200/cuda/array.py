@@ -15,6 +15,7 @@ copy, fill, item, get, __getitem__/__setitem__, + * @ ** / unary -, and comparis
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 from typing import Optional, Sequence, Tuple, Union
 
@@ -33,27 +34,46 @@ class _Block:
 
     def __init__(self, nbytes: int) -> None:
         self.ptr = None
-        _capi.require_device()
+        if not _capi._DEVICE_READY:
+            _capi.require_device()
         p = C.c_void_p()
-        _capi.check(_capi.lib().mt_malloc(C.byref(p), max(int(nbytes), 1)), "mt_malloc")
+        status = _capi._LIB.mt_malloc(C.byref(p), nbytes if nbytes > 0 else 1)
+        if status:
+            _capi.check(status, "mt_malloc")
         self.ptr = p.value
-        self.nbytes = int(nbytes)
+        self.nbytes = nbytes
 
     def __del__(self) -> None:
         ptr, self.ptr = getattr(self, "ptr", None), None
         if ptr:
             try:
-                _capi.lib().mt_free(ptr)
+                _capi._LIB.mt_free(ptr)
             except Exception:       # interpreter teardown
                 pass
 
 
-def _dense_strides(shape: Sequence[int]) -> Tuple[int, ...]:
+@functools.lru_cache(maxsize=8192)
+def _dense_strides_cached(shape: tuple) -> Tuple[int, ...]:
     st, acc = [], 1
     for d in reversed(shape):
         st.append(acc)
         acc *= max(int(d), 1)
     return tuple(reversed(st))
+
+
+def _dense_strides(shape: Sequence[int]) -> Tuple[int, ...]:
+    return _dense_strides_cached(shape if type(shape) is tuple else tuple(shape))
+
+
+def _int_tuple(seq) -> Tuple[int, ...]:
+    """Shape / stride tuple of Python ints (no work when it already is one: the per-launch host path)."""
+    if type(seq) is tuple:
+        for d in seq:
+            if type(d) is not int:
+                break
+        else:
+            return seq
+    return tuple(int(d) for d in seq)
 
 
 def _numel(shape: Sequence[int]) -> int:
@@ -64,27 +84,29 @@ def _numel(shape: Sequence[int]) -> int:
 
 
 class DeviceArray:
-    __slots__ = ("_block", "ptr", "shape", "strides", "dtype", "_host_value", "_owned", "_const", "__weakref__")
+    __slots__ = ("_block", "ptr", "shape", "strides", "dtype", "_host_value", "_owned", "_const", "_dense", "__weakref__")
     __array_priority__ = 1000       # numpy scalars defer to our reflected operators
 
     def __init__(self, block: _Block, ptr: int, shape: Sequence[int], strides: Sequence[int],
                  dtype: np.dtype = F32) -> None:
         self._block = block
         self.ptr = ptr
-        self.shape = tuple(int(d) for d in shape)
-        self.strides = tuple(int(s) for s in strides)      # in ELEMENTS
-        self.dtype = np.dtype(dtype)
+        self.shape = _int_tuple(shape)
+        self.strides = _int_tuple(strides)                  # in ELEMENTS
+        self.dtype = dtype if dtype is F32 else np.dtype(dtype)
         self._host_value = None     # host mirror of a 0-d constant built from a Python scalar
         self._owned = False         # adopted as some tensor's .grad (see Tensor._receive)
         self._const = False         # shared read-only constant (device_constant): never adopted, never written
+        self._dense = None          # cached is_dense (shape and strides never change after construction)
 
     # ------------------------------------------------------------------ constructors
     @classmethod
     def empty(cls, shape: Sequence[int], dtype: np.dtype = F32) -> "DeviceArray":
-        shape = tuple(int(d) for d in shape)
-        dtype = np.dtype(dtype)
+        shape = _int_tuple(shape)
+        if dtype is not F32:
+            dtype = np.dtype(dtype)
         blk = _Block(_numel(shape) * dtype.itemsize)
-        return cls(blk, blk.ptr, shape, _dense_strides(shape), dtype)
+        return cls(blk, blk.ptr, shape, _dense_strides_cached(shape), dtype)
 
     @classmethod
     def zeros(cls, shape: Sequence[int], dtype: np.dtype = F32) -> "DeviceArray":
@@ -131,12 +153,16 @@ class DeviceArray:
     @property
     def is_dense(self) -> bool:
         """C-contiguous (extent-1 dims are free)."""
-        acc = 1
-        for d, s in zip(reversed(self.shape), reversed(self.strides)):
-            if d != 1 and s != acc:
-                return False
-            acc *= d
-        return True
+        dense = self._dense
+        if dense is None:
+            dense, acc = True, 1
+            for d, s in zip(reversed(self.shape), reversed(self.strides)):
+                if d != 1 and s != acc:
+                    dense = False
+                    break
+                acc *= d
+            self._dense = dense
+        return dense
 
     def _view(self, shape, strides, ptr=None) -> "DeviceArray":
         return DeviceArray(self._block, self.ptr if ptr is None else ptr, shape, strides, self.dtype)
@@ -220,7 +246,9 @@ class DeviceArray:
             shape = tuple(shape[0])
         elif len(shape) == 1 and shape[0] is None:
             shape = ()
-        shape = tuple(int(d) for d in shape)
+        shape = _int_tuple(shape)
+        if shape == self.shape:
+            return self
         n = self.size
         if -1 in shape:
             known = -_numel(shape)
@@ -229,6 +257,8 @@ class DeviceArray:
             shape = tuple(n // known if d == -1 else d for d in shape)
         if _numel(shape) != n:
             raise ValueError(f"cannot reshape array of size {n} into shape {shape}")
+        if shape == self.shape:
+            return self
         src = self.dense()                      # NumPy copies too when a view cannot express it
         return src._view(shape, _dense_strides(shape))
 
@@ -274,7 +304,9 @@ class DeviceArray:
         return self._view(shape, strides)
 
     def broadcast_to(self, shape) -> "DeviceArray":
-        shape = tuple(int(d) for d in shape)
+        shape = _int_tuple(shape)
+        if shape == self.shape:
+            return self
         if len(shape) < self.ndim:
             raise ValueError("input operand has more dimensions than allowed by the axis remapping")
         lead = len(shape) - self.ndim

@@ -19,6 +19,12 @@ def _lib():
 
 # ----------------------------------------------------------------------------- elementwise
 def broadcast_shape(a: Sequence[int], b: Sequence[int]) -> Tuple[int, ...]:
+    if a == b:
+        return a if type(a) is tuple else tuple(a)
+    if len(b) == 0:
+        return a if type(a) is tuple else tuple(a)
+    if len(a) == 0:
+        return b if type(b) is tuple else tuple(b)
     return tuple(np.broadcast_shapes(tuple(a), tuple(b)))
 
 
@@ -32,9 +38,10 @@ def binary(op: int, a, b, scalar: float = 0.0, out: Optional[DeviceArray] = None
     elif out.shape != shape or not out.is_dense:
         raise ValueError("binary(out=): output must be a dense array of the broadcast shape")
     if out.size:
-        _capi.check(_lib().mt_ew_binary_f32(op, out.ptr, av.ptr, bv.ptr, len(shape), _capi.i64(shape),
-                                            _capi.i64(av.strides), _capi.i64(bv.strides), float(scalar)),
-                    "mt_ew_binary_f32")
+        status = _lib().mt_ew_binary_f32(op, out.ptr, av.ptr, bv.ptr, len(shape), _capi.i64(shape), _capi.i64(av.strides),
+                                         _capi.i64(bv.strides), float(scalar))
+        if status:
+            _capi.check(status, "mt_ew_binary_f32")
     return out
 
 

@@ -81,6 +81,18 @@ def op_gate(fn):
     return input_gate(from_op(fn))
 
 
+_DEVICE_ARRAY = None
+
+
+def _device_array_type():
+    """microtorch_b200.cuda.DeviceArray, resolved on first use (a CUDA tensor implies the namespace is importable)."""
+    global _DEVICE_ARRAY
+    if _DEVICE_ARRAY is None:
+        from ..cuda.array import DeviceArray
+        _DEVICE_ARRAY = DeviceArray
+    return _DEVICE_ARRAY
+
+
 class _LazyZero:
     """Marker: "this tensor's gradient is all zeros and has not been allocated yet"."""
     __slots__ = ()
@@ -93,7 +105,10 @@ _LAZY = _LazyZero()
 
 
 @final
-class Tensor(TensorLike):
+class Tensor:
+    # Satisfies the `TensorLike` protocol structurally (isinstance(t, TensorLike) holds) but does not inherit from it:
+    # a Protocol base gives the class typing's metaclass, and then every isinstance(x, Tensor / Parameter) on the
+    # per-step host path (Module.parameters, the gates) costs a structural check instead of a pointer compare.
     float64 = DType.FLOAT64
     float32 = DType.FLOAT32
     int64 = DType.INT64
@@ -103,10 +118,15 @@ class Tensor(TensorLike):
 
     def __init__(self, data: Data, requires_grad: bool = False, dependencies: Optional[DependenciesList] = None,
                  device: Union[Device, str] = Device.CPU, dtype: Optional[DType] = None) -> None:
-        self._device = _device(device)
+        self._device = device if type(device) is Device else _device(device)
         self._dtype = dtype or DType.FLOAT32
         self._dependencies: DependenciesList = dependencies or []
-        self._data_ = self.build_ndarray(data, self._dtype, self._device)
+        # per-op host path: the result array of an op already is a native float32 array of this device
+        if (self._dtype is DType.FLOAT32 and self._device is Device.CUDA and type(data) is _device_array_type()
+                and data.dtype == np.float32):
+            self._data_ = data
+        else:
+            self._data_ = self.build_ndarray(data, self._dtype, self._device)
         self._requires_grad = requires_grad
         self._grad = None
         self._grad_hook: Optional[Callable[["Tensor"], None]] = None

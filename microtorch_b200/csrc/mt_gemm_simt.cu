@@ -185,6 +185,7 @@ int launch(const GemmArgs& a, long long batch) {
 namespace mt {
 
 static int g_skinny = 1;   // test hook: 0 routes tiny-N shapes through the generic tile as well
+static int g_small_tiles = 1;   // test hook: 0 keeps the 128x128 tile for small problems (mt_gemm_set_small_tiles)
 
 int splitk_finalize(float* C, const float* partial, int splits, long long M, long long N, const float* bias, int act,
                     int accumulate, const float* epi_tanh) {
@@ -213,13 +214,21 @@ int gemm_simt(GemmArgs a, long long batch) {
     if (rc != MT_ERR_UNSUPPORTED) return rc;
   }
   // tile choice
-  int shape = 0;  // 0: 128x128, 1: 256x16 (skinny N), 2: 16x256 (skinny M)
+  int shape = 0;  // 0: 128x128, 1: 256x16 (skinny N), 2: 16x256 (skinny M), 3: 64x64, 4: 32x32
+  const long long sms = g().sm_count;
   if (a.N <= 16 && a.M >= 64) shape = 1;
   else if (a.M <= 16 && a.N >= 64) shape = 2;
-  const long long bm = shape == 0 ? 128 : (shape == 1 ? 256 : 16), bn = shape == 0 ? 128 : (shape == 1 ? 16 : 256);
+  else if (g_small_tiles) {
+    // small problems (the 200-row layers of the spiral demo): a 128x128 tile leaves one or two CTAs on 148 SMs, each
+    // thread grinding through 64 mostly-padding outputs (30-60 us per launch measured); smaller tiles spread the same
+    // work over more SMs and skip the padding
+    if (ceil_div(a.M, 128) * ceil_div(a.N, 128) * batch < sms)
+      shape = (ceil_div(a.M, 64) * ceil_div(a.N, 64) * batch >= sms) ? 3 : 4;
+  }
+  const long long bm = shape == 0 ? 128 : (shape == 1 ? 256 : (shape == 2 ? 16 : (shape == 3 ? 64 : 32)));
+  const long long bn = shape == 0 ? 128 : (shape == 1 ? 16 : (shape == 2 ? 256 : (shape == 3 ? 64 : 32)));
   const long long tiles = ceil_div(a.M, bm) * ceil_div(a.N, bn) * batch;
   long long splits = 1;
-  const long long sms = g().sm_count;
   if (batch == 1 && tiles < 2 * sms && a.K >= 1024) {
     splits = std::min<long long>(ceil_div(2 * sms, tiles), a.K / 256);
     if (splits > 65535) splits = 65535;
@@ -240,7 +249,9 @@ int gemm_simt(GemmArgs a, long long batch) {
   int rc;
   if (shape == 0) rc = launch<128, 128, 8, 8>(a, batch);
   else if (shape == 1) rc = launch<256, 16, 4, 4>(a, batch);
-  else rc = launch<16, 256, 4, 4>(a, batch);
+  else if (shape == 2) rc = launch<16, 256, 4, 4>(a, batch);
+  else if (shape == 3) rc = launch<64, 64, 4, 4>(a, batch);
+  else rc = launch<32, 32, 2, 2>(a, batch);
   if (rc) return rc;
   if (splits > 1) {
     rc = splitk_finalize(final_c, partial.f32(), (int)splits, a.M, a.N, a.bias, a.act, a.accumulate, a.epi_tanh);
@@ -269,6 +280,11 @@ MT_API int mt_matmul_f32(float* C, const float* A, const float* B, int64_t batch
   }
   g().gemm_last_engine = 0;
   return gemm_simt(a, batch);
+}
+
+extern "C" __attribute__((visibility("default"))) int mt_gemm_set_small_tiles(int v) {
+  mt::g_small_tiles = v ? 1 : 0;
+  return MT_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int mt_gemm_set_skinny(int v) {

@@ -195,6 +195,13 @@ class DeviceArray:
     def __repr__(self) -> str:
         return f"DeviceArray({np.array2string(self.get(), separator=', ')}, dtype={self.dtype.name})"
 
+    def __str__(self) -> str:
+        """Like the host array (the notebook prints `data_loss.data` inside an f-string, demo.ipynb:5186)."""
+        return str(self.get())
+
+    def __format__(self, spec: str) -> str:
+        return format(self.get(), spec)
+
     def __len__(self) -> int:
         if not self.shape:
             raise TypeError("len() of unsized object")

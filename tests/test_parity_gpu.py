@@ -59,6 +59,8 @@ def test_tensor_roundtrip_and_props(mt):
     assert t.device.value == "cuda" and t.shape == (5, 7) and t.ndim == 2 and t.size == 35
     np.testing.assert_array_equal(host(t.data), x)
     np.testing.assert_array_equal(host(t.grad), np.zeros_like(x))          # zero grad visible after construction
+    s0 = t.sum()
+    assert abs(float(f"{s0.data}") - float(x.sum())) < 1e-3 and f"{s0.data:.3f}" == f"{float(s0.item()):.3f}"   # prints like NumPy
     back = t.to("cpu")
     np.testing.assert_array_equal(back.data, x)
     assert mt.Tensor(3.5, device="cuda").item() == 3.5

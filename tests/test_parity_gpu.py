@@ -806,3 +806,51 @@ def test_full_size_step_against_the_oracle(mt):
     import full_size_parity
     rec = full_size_parity.run()
     assert rec["pass"], rec
+
+
+def test_user_level_notebook_flow_on_cuda(mt):
+    """The way the notebook uses the library (demo.ipynb:104-131, 5170-5189, 5199-5210), written out by hand against
+    this package on device="cuda": a Module subclass that never calls super().__init__(), an optimizer built from the
+    bound `parameters` method, first-call device migration, `.squeeze(1)`, an f-string over `loss.data`, `eval()`,
+    and a grid prediction brought back with `.to("cpu").data.reshape(...)`.  Losses vs the notebook's published stream."""
+    import random
+    from microtorch_b200.nn import Module
+
+    class MLP(Module):
+        def __init__(self, inputs, outputs, lr=0.5):
+            tail = []                        # the notebook creates the later layers FIRST (RNG order matters)
+            for a, b in zip(outputs[:-1], outputs[1:]):
+                tail += [mt.Linear(a, b), mt.Tanh()]
+            self.layers = mt.Sequential(mt.Linear(inputs, outputs[0]), mt.Tanh(), *tail)
+            self._optimizer = mt.SGD(self.layers.parameters, lr=lr)
+
+        @property
+        def optimizer(self):
+            return self._optimizer
+
+        def forward(self, x):
+            return self.layers(x)
+
+    np.random.seed(1337)
+    random.seed(1337)
+    X, y = W.spiral_dataset(200, 0.9)
+    model = MLP(2, [64, 32, 16, 1])
+    assert model.params_count() == 2817
+    X_train, y_train = mt.Tensor(X, device="cuda"), mt.Tensor(y, device="cuda")
+    loss = mt.losses["mse"]()
+    printed = []
+    for step in range(12):
+        model.zero_grad()
+        y_pred = model(X_train)
+        data_loss = loss(y_pred.squeeze(1), y_train)
+        data_loss.backward()
+        model.optimizer.step()
+        printed.append(f"Step {step}, loss: {data_loss.data}")
+    pub = json.load(open(os.path.join(GOLDEN, "c1a_notebook_losses.json")))["losses"]
+    for step, line in enumerate(printed):
+        got = float(line.split("loss: ")[1])
+        assert abs(got - float(pub[str(step)])) <= 1e-5 * abs(float(pub[str(step)])), line
+    model.eval()
+    grid = np.c_[np.linspace(-1, 1, 50), np.linspace(1, -1, 50)]
+    Z = model(mt.Tensor(grid, device="cuda")).to("cpu").data.reshape(5, 10)
+    assert isinstance(Z, np.ndarray) and Z.shape == (5, 10) and np.all(np.abs(Z) <= 1.0)

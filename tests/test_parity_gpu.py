@@ -854,3 +854,18 @@ def test_user_level_notebook_flow_on_cuda(mt):
     grid = np.c_[np.linspace(-1, 1, 50), np.linspace(1, -1, 50)]
     Z = model(mt.Tensor(grid, device="cuda")).to("cpu").data.reshape(5, 10)
     assert isinstance(Z, np.ndarray) and Z.shape == (5, 10) and np.all(np.abs(Z) <= 1.0)
+
+
+def test_training_is_run_to_run_deterministic(mt):
+    """No float atomics anywhere (split-K partials, reductions, the loss and the on-chip trainer's exchange are folded in
+    a fixed order): two independent runs of the same steps end in bit-identical losses, weights and gradients - on the
+    tensor-core path with split-K and the skinny head, and in the single-launch trainer."""
+    wl = W.scaled(W.C2, 2048, (1024, 512, 256, 10))
+    a, b = run_cuda(mt, wl, 3), run_cuda(mt, wl, 3)
+    np.testing.assert_array_equal(a["losses"], b["losses"])
+    for x, y in zip(a["params"] + a["grads"], b["params"] + b["grads"]):
+        np.testing.assert_array_equal(x, y)
+    c, d = run_fit(mt, W.C1A, 50, fused=True), run_fit(mt, W.C1A, 50, fused=True)
+    np.testing.assert_array_equal(c["losses"], d["losses"])
+    for x, y in zip(c["params"], d["params"]):
+        np.testing.assert_array_equal(x, y)

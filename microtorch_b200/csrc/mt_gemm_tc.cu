@@ -738,9 +738,14 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   int S = 1;
   if (g_splitk && tiles < 8 * unit_count) {
     double best = 0.0;
+    // multi-wave problems keep >= 64 k-blocks per split (the fold pass must stay negligible); a problem that does not
+    // even fill one wave is latency-bound on its serial K loop (~1.1 us per k-block, tools/engine_crossover.py), so idle
+    // units take K slices down to one accumulation chunk (8 k-blocks) each
+    const int min_kb = tiles < unit_count ? 8 : 64;
     for (int s = 1; s <= 8; ++s) {
-      if (s > 1 && p.k_blocks / s < 64) break;
+      if (s > 1 && p.k_blocks / s < min_kb) break;
       const long long work = tiles * s;
+      if (s > 1 && tiles < unit_count && work > unit_count) break;      // single-wave case: never spill into a 2nd wave
       const double eff = (double)work / (double)(ceil_div(work, unit_count) * unit_count);
       if (eff > best + 0.02) { best = eff; S = s; }
       if (best >= 0.95) break;
@@ -839,9 +844,10 @@ int gemm_tc_try(const GemmArgs& a) {
   // worthwhile shapes only: small / skinny problems are SIMT territory (HBM- or latency-bound)
   if (g().gemm_engine_force != 1) {
     if (a.M < 128 || a.N < 64 || a.K < 32) return MT_ERR_UNSUPPORTED;
-    // below ~16 M multiply-adds the 512-thread / 227 KB / TMEM kernel is pure launch latency (14 us measured on the
-    // 200x64x32 spiral-demo layers): the SIMT tile finishes sooner
-    if (a.M * a.N * a.K < (1ll << 24)) return MT_ERR_UNSUPPORTED;
+    // measured crossover (tools/engine_crossover.py, profiles/r01_engine_crossover.jsonl): a tile's serial K loop plus
+    // the 512-thread / 227 KB / TMEM launch cost ~12 us + ~1 us per k-block, so below 2^28 multiply-adds the SIMT tile
+    // (64x64 / 32x32 tiles spread over the SMs) finishes first - by 1.5-2.4x at 2^26 - and from 2^28 up tcgen05 wins
+    if (a.M * a.N * a.K < (1ll << 28)) return MT_ERR_UNSUPPORTED;
   } else if (a.M < 1 || a.N < 4 || a.K < 1) {
     return MT_ERR_UNSUPPORTED;
   }

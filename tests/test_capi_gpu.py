@@ -301,14 +301,21 @@ def test_linear_ragged_shapes_on_tensor_cores(lib, M, N, K):
     dY = rng.standard_normal((M, N)).astype(np.float32)
     Xd, Wd, bd, dYd, Y = Dev(X), Dev(W), Dev(b), Dev(dY), Dev(shape=(M, N))
     eng = C.c_int(-5)
-    _capi.check(lib.mt_linear_fwd_f32(Y.ptr, Xd.ptr, Wd.ptr, bd.ptr, M, N, K, 1))
-    lib.mt_gemm_last_engine(C.byref(eng))
-    # the tensor-core path stores 128-bit rows: N % 4 != 0 is served by the SIMT tile (still checked below)
-    assert eng.value == (1 if N % 4 == 0 else 0), "unexpected GEMM engine for this shape"
-    Yh = Y.get()
-    assert gemm_err(Yh, np.tanh(X.astype(np.float64) @ W.astype(np.float64).T + b)) < 2e-5
-    dX, dW = Dev(shape=(M, K)), Dev(np.full((N, K), 0.5, np.float32))
-    _capi.check(lib.mt_linear_bwd_f32(dX.ptr, dW.ptr, dYd.ptr, Y.ptr, Xd.ptr, Wd.ptr, M, N, K, 1 | 2))
+    # the shapes are below the size at which the dispatcher prefers tcgen05, so the engine is forced where the kernel can
+    # take the shape at all (it stores 128-bit rows: N % 4 != 0 is served by the SIMT tile - still checked below)
+    lib.mt_gemm_set_engine(1 if N % 4 == 0 else -1)
+    try:
+        _capi.check(lib.mt_linear_fwd_f32(Y.ptr, Xd.ptr, Wd.ptr, bd.ptr, M, N, K, 1))
+        lib.mt_gemm_last_engine(C.byref(eng))
+        assert eng.value == (1 if N % 4 == 0 else 0), "unexpected GEMM engine for this shape"
+        Yh = Y.get()
+        assert gemm_err(Yh, np.tanh(X.astype(np.float64) @ W.astype(np.float64).T + b)) < 2e-5
+        dX, dW = Dev(shape=(M, K)), Dev(np.full((N, K), 0.5, np.float32))
+        _capi.check(lib.mt_linear_bwd_f32(dX.ptr, dW.ptr, dYd.ptr, Y.ptr, Xd.ptr, Wd.ptr, M, N, K, 1 | 2))
+        lib.mt_gemm_last_engine(C.byref(eng))
+        assert eng.value == (1 if N % 4 == 0 else 0)
+    finally:
+        lib.mt_gemm_set_engine(-1)
     dz = dY.astype(np.float64) * (1 - Yh.astype(np.float64) ** 2)
     assert gemm_err(dW.get(), dz.T @ X + 0.5) < 2e-5
     assert gemm_err(dX.get(), (dz @ W) * (1 - X.astype(np.float64) ** 2)) < 2e-5

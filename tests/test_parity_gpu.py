@@ -597,7 +597,7 @@ def test_bare_matmul_views_on_tensor_cores(mt):
     all four operand-major combinations, a row-sliced operand (pitch > extent), forward and both gradients."""
     import ctypes as C
     rng = np.random.default_rng(40)
-    M, K, N = 512, 384, 256
+    M, K, N = 1024, 768, 512          # 2^28.6 multiply-adds: above the size where the dispatcher picks tcgen05
     for ta in (False, True):
         for tb in (False, True):
             av = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)

@@ -121,7 +121,7 @@ def main():
                           "samples_per_s": wl.batch * steps / (ms.value / 1e3), "launches": 1,
                           "last_loss": float(ls[-1])}), flush=True)
 
-    want = lambda k: (not args.only and k != "c1fit") or k in args.only.split(",")
+    want = lambda k: (not args.only and k not in ("c1fit", "mid")) or k in args.only.split(",")
     if want("c1fit"):
         run_single_launch(W.C1A, 5000, "c1a_spiral_notebook_mlp_2_64_32_16_1")
         run_single_launch(W.C1B, 5000, "c1b_spiral_2_100_3")
@@ -133,6 +133,12 @@ def main():
         run(W.C1B, 2000, 50, "c1b_spiral_2_100_3")
         run_graphed(W.C1B, 5000, "c1b_spiral_2_100_3")
         run_single_launch(W.C1B, 5000, "c1b_spiral_2_100_3")
+    if want("mid"):      # between the on-chip trainer and the big persistent GEMM: a few thousand rows, a few hundred features
+        for batch, dims in ((4096, (256, 512, 512, 10)), (8192, (784, 1024, 1024, 10)), (1024, (128, 256, 256, 10))):
+            wl = W.scaled(W.C2, batch, dims)
+            tag = "mid_mlp_" + "_".join(map(str, dims)) + f"_b{batch}"
+            run(wl, 200, 20, tag, {"gemm_flops_per_step": wl.gemm_flops_per_step()})
+            run_graphed(wl, 500, tag)
     if want("c4"):
         k = args.c4_layers
         wl = W.Workload("c4", (2048,) * (k + 1), "bce", 0.01, 256, pred_map=(0.49, 0.5), seed=0, input_shape=(256, 512, 2048))

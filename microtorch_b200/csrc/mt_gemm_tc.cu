@@ -32,6 +32,7 @@
 // Roofline: tensor pipe (91-99 % active in the ncu captures under profiles/).  One k-block (32) of a 256x256 pair
 // tile is 12 tcgen05.mma (M256 N256 K8), 128 cycles each; logical 2*M*N*K flops are reported against (TF32 peak)/3.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <algorithm>
 #include <vector>
@@ -202,6 +203,25 @@ __device__ __forceinline__ void umma_tf32_n(uint32_t d_tmem, uint64_t adesc, uin
         : "memory");
   }
 }
+// 16-bit inputs (bf16 here), fp32 accumulate: K = 16 per instruction
+template <int NCTA>
+__device__ __forceinline__ void umma_f16_n(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (NCTA == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
 // tcgen05.commit: 1-CTA -> own barrier; CTA pair -> the barrier at the same offset in BOTH CTAs
 template <int NCTA>
 __device__ __forceinline__ void umma_commit_n(uint32_t bar) {
@@ -239,6 +259,21 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool a_mn, bool 
          (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 
+// "mix" mode (hi.hi on TF32, the two first-order corrections on BF16 at twice the rate): the correction operands are
+// 16-bit K-major tiles of 32 k (64-byte rows) in SWIZZLE_64B (type 4): 8-row atoms 512 B apart (SBO), one UMMA_K slice
+// (16 k) = 32 B further along the row.
+// MN-major correction tiles: 32 (mn) x 32 (k) boxes of 2048 B (LBO: next 32 mn), 8-row k-atoms 512 B apart (SBO), one
+// UMMA_K slice (16 k) = 1024 B further.
+__host__ __device__ constexpr uint64_t make_smem_desc_base_16(bool mn_major) {
+  return mn_major ? ((uint64_t(2048 >> 4) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(4) << 61))
+                  : ((uint64_t(1) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(4) << 61));
+}
+// D=f32, A=B=bf16
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) | (uint32_t(n >> 3) << 17) |
+         (uint32_t(m >> 4) << 24);
+}
+
 struct Params {
   float* C;
   const float* bias;
@@ -251,6 +286,7 @@ struct Params {
   int splits, kb_per_split;    // split-K: work item = (tile, split); split s covers k-blocks [s*kbps, (s+1)*kbps)
                                // and writes its partial to C + s*M*N (folded by splitk_finalize)
   int raw_stages, lo_stages;   // ring depths (runtime: the split of the 227 KB is a tuning knob)
+  int mix;            // 1: corrections as BF16 products from K-major [A_hi16 | A_lo16 | B_hi16 | B_lo16] tiles in the lo ring
   int dbg;            // timing experiments only (results are wrong): 1 skip the conversion, 2 issue hi*hi only,
                       // 4 issue no MMA at all
 };
@@ -311,6 +347,73 @@ __device__ __forceinline__ void convert_tile(uint8_t* raw_b, uint8_t* lo_b, int 
     for (int u = 0; u < U; ++u) {
       if (WRITE_HI) raw[ct + (b + u) * 128] = h[u];
       lo[ct + (b + u) * 128] = l[u];
+    }
+  }
+}
+// mix mode, K-major source: the fp32 tile (SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)) is split
+// into bf16(x) and bf16(x - trunc_tf32(x)) and written as two SWIZZLE_64B tiles (64-byte rows; 16-byte chunk q of row r
+// sits at chunk q ^ ((r >> 1) & 3)).  A thread keeps its physical source chunk, so the logical column and the
+// destination offset inside the row are per-thread constants; rows advance by 16 per step.
+template <int VECS>
+__device__ __forceinline__ void convert_tile_mix_k(const uint8_t* raw_b, uint8_t* hi16_b, uint8_t* lo16_b, int ct) {
+  constexpr int PER = VECS / 128;
+  constexpr int U = PER < 4 ? PER : 4;
+  const float4* raw = reinterpret_cast<const float4*>(raw_b);
+  const int c = (ct & 7) ^ ((ct >> 3) & 7);                               // logical 16-byte chunk: k = 4c .. 4c+3
+  const int dst0 = (ct >> 3) * 64 + ((((c >> 1) ^ ((ct >> 4) & 3))) << 4) + ((c & 1) << 3);
+#pragma unroll
+  for (int b = 0; b < PER; b += U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = raw[ct + (b + u) * 128];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4 x = v[u];
+      float4 lo;
+      lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+      lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+      lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+      lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+      __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
+      const int off = dst0 + (b + u) * 1024;
+      *reinterpret_cast<uint2*>(hi16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(lo16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+    }
+  }
+}
+// mix mode, MN-major source (dW / dX operands): the raw tile is ROWS/32 TMA boxes of 32 (mn) x 32 (k) floats in
+// SWIZZLE_128B_ATOM_32B = Swizzle<2,5,2>: row k of a box is 128 B = 32 mn, and the 32-byte chunk c of row k sits at chunk
+// c ^ (k & 3).  The correction tiles stay MN-major: boxes of 32 (k) rows x 64 B (32 mn as bf16) in SWIZZLE_64B =
+// Swizzle<2,4,3> (16-byte chunk q of row k sits at q ^ ((k >> 1) & 3)).  Four consecutive mn are 16 B of the source and
+// 8 B of the destination, and the 32-byte source chunk index equals the 16-byte destination chunk index, so the
+// conversion is element-wise on the byte image again: contiguous loads, contiguous 8-byte stores, no transpose.
+template <int ROWS>
+__device__ __forceinline__ void convert_tile_mix_mn(const uint8_t* raw_b, uint8_t* hi16_b, uint8_t* lo16_b, int ct) {
+  constexpr int PER = ROWS * 8 / 128;                    // float4 per thread
+  constexpr int U = PER < 4 ? PER : 4;
+  const float4* raw = reinterpret_cast<const float4*>(raw_b);
+#pragma unroll
+  for (int b = 0; b < PER; b += U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = raw[ct + (b + u) * 128];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = ct + (b + u) * 128;
+      const int box = i >> 8, k = (i & 255) >> 3, p16 = i & 7;
+      const int c32 = (p16 >> 1) ^ (k & 3);
+      const int off = box * 2048 + k * 64 + ((c32 ^ ((k >> 1) & 3)) << 4) + ((p16 & 1) << 3);
+      const float4 x = v[u];
+      float4 lo;
+      lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+      lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+      lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+      lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+      __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
+      *reinterpret_cast<uint2*>(hi16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      *reinterpret_cast<uint2*>(lo16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
     }
   }
 }
@@ -482,6 +585,25 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               const uint32_t sb = sa + C::A_TILE;
               const uint32_t sa_lo = lo_base + lo * C::LO_STAGE;
               const uint32_t sb_lo = sa_lo + C::A_TILE;
+              if (!PRO && p.mix) {
+                // mix mode: two BF16 correction products (2 x K16 each), then hi.hi on TF32 (4 x K8)
+                constexpr uint32_t idesc16 = make_idesc_bf16(BM * NCTA, BN, A_MN, B_MN);
+                constexpr uint64_t da16 = make_smem_desc_base_16(A_MN), db16 = make_smem_desc_base_16(B_MN);
+                constexpr uint32_t a16step = A_MN ? 1024u : 32u, b16step = B_MN ? 1024u : 32u;   // bytes per K16 slice
+                const uint32_t a16hi = sa_lo, a16lo = sa_lo + C::A_TILE / 2;
+                const uint32_t b16hi = sb_lo, b16lo = sb_lo + C::B_TILE / 2;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  umma_f16_n<NCTA>(d_tmem, smem_desc(da16, a16lo + j * a16step), smem_desc(db16, b16hi + j * b16step), idesc16,
+                                   (kb > kb0) || (j > 0));
+                  umma_f16_n<NCTA>(d_tmem, smem_desc(da16, a16hi + j * a16step), smem_desc(db16, b16lo + j * b16step), idesc16,
+                                   1u);
+                }
+#pragma unroll
+                for (int j = 0; j < BK / UMMA_K; ++j)
+                  umma_tf32_n<NCTA>(d_tmem, smem_desc(adesc_base, sa + j * a_kstep), smem_desc(bdesc_base, sb + j * b_kstep),
+                                    idesc, 1u);
+              } else
 #pragma unroll
               for (int j = 0; j < BK / UMMA_K; ++j) {
                 const uint64_t a_hi = smem_desc(adesc_base, sa + j * a_kstep);
@@ -522,11 +644,18 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (p.dbg & 1) {
             // timing experiment: hand the stage over untouched
           } else {
+            if (!PRO && p.mix) {
+              if (A_MN) convert_tile_mix_mn<BM>(sa, sa_lo, sa_lo + C::A_TILE / 2, ct);
+              else convert_tile_mix_k<C::A_TILE / 16>(sa, sa_lo, sa_lo + C::A_TILE / 2, ct);
+              if (B_MN) convert_tile_mix_mn<C::BN_LOCAL>(sb, sb_lo, sb_lo + C::B_TILE / 2, ct);
+              else convert_tile_mix_k<C::B_TILE / 16>(sb, sb_lo, sb_lo + C::B_TILE / 2, ct);
+            } else {
             if (PRO) convert_tile_prologue<C::A_TILE / 16>(sa, sy, sa_lo, ct);
             else if (p.write_hi) convert_tile<C::A_TILE / 16, true>(sa, sa_lo, ct);
             else convert_tile<C::A_TILE / 16, false>(sa, sa_lo, ct);
             if (p.write_hi) convert_tile<C::B_TILE / 16, true>(sb, sb_lo, ct);
             else convert_tile<C::B_TILE / 16, false>(sb, sb_lo, ct);
+            }
           }
           fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
@@ -685,6 +814,7 @@ static int g_dbg_flags = 0;   // Params::dbg
 static int g_splitk = 1;      // allow split-K for badly quantised tile counts
 static int g_lo_stages = 3;   // lo ring depth; the raw ring gets whatever else fits (or g_raw_stages if > 0)
 static int g_raw_stages = 0;
+static int g_mix = 1;         // 1 (default): hi.hi on TF32, the two first-order corrections as BF16 products; 0: 3xTF32
 static int g_pair = 1;        // 1: CTA pairs (cta_group::2) for N > 128 when the shape allows; 0: single CTAs only
 
 template <int BN, bool A_MN, bool B_MN, int NCTA, bool PRO>
@@ -717,6 +847,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   p.k_blocks = (int)ceil_div(a.K, BK);
   p.chunk_kb = g_chunk_kb > 0 ? g_chunk_kb : p.k_blocks;
   p.write_hi = g_write_hi;
+  p.mix = (g_mix && !PRO && !g_write_hi) ? 1 : 0;
   p.dbg = g_dbg_flags;
   {  // ring depths: lo ring g_lo_stages deep (default 3), raw ring takes the rest of the 227 KB
     int l = g_lo_stages, r = g_raw_stages;
@@ -919,5 +1050,9 @@ extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_pair(int v)
 }
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_chunk_kb(int v) {
   tc::g_chunk_kb = v < 0 ? 0 : v;
+  return MT_OK;
+}
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_mix(int v) {
+  tc::g_mix = v ? 1 : 0;
   return MT_OK;
 }

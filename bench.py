@@ -14,7 +14,7 @@ gradients are all-reduced with NCCL.  Rank 0 prints ONE JSON line.
   value      samples/s over all GPUs, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        same metric through the public API with HOST inputs: every step uploads X,T from
              pinned host memory and reads the loss back
-  roofline   the dominant kernel (tcgen05 3xTF32 GEMM): logical 2MNK flops / device time measured
+  roofline   the dominant kernel (tcgen05 split-fp32 GEMM): logical 2MNK flops / device time measured
              live with CUDA events around every GEMM launch of the timed region
   cpu_baseline / --impl reference   the oracle port of the reference's NumPy path on the host cores,
              on a bounded sample (batch 4096) of the same workload
@@ -333,7 +333,10 @@ def main():
         return
 
     peaks = load_peaks()
-    peak_tf = peaks["bf16_sustained"] / 2.0 / 3.0        # fp32-emulated (3xTF32) = TF32 dense / 3 = bf16 / 6
+    # fp32-emulated peak: one logical multiply-add costs one TF32 product (= 2 bf16-rate units) for hi.hi plus two BF16
+    # products for the first-order corrections = 4 units, so the logical peak is (bf16 dense peak) / 4
+    EMU = 4.0
+    peak_tf = peaks["bf16_sustained"] / EMU
     achieved_tf = (gemm_flops.value / n_gemm.value) / ((gemm_ms.value / n_gemm.value) * 1e-3) / 1e12 if n_gemm.value else 0.0
     out = {
         "metric": "mlp_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -342,7 +345,7 @@ def main():
         "config": {"workload": ("c2_mlp_1024_4096_4096_10_tanh_ce_sgd" if args.workload == "c2" else "c5_mlp_4096x8_tanh_mse_sgd"),
                    "per_gpu_batch": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (activations 1 GiB per layer); no flush needed",
-                   "gemm": "tcgen05 3xTF32, chunked TMEM accumulation"},
+                   "gemm": "tcgen05 split-fp32 (TF32 hi.hi + 2 BF16 corrections per k-slice), chunked TMEM accumulation"},
         "loss": loss_value,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.nbytes + t_host.nbytes) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
@@ -350,14 +353,14 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm3xtf32_kernel (tcgen05)", "achieved": achieved_tf, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
-                     "frac_of_burst_peak": achieved_tf / (peaks["bf16"] / 6.0) if peaks["bf16"] else None,
+                     "frac_of_burst_peak": achieved_tf / (peaks["bf16"] / EMU) if peaks["bf16"] else None,
                      "traffic": ncu_traffic_per_launch(),
                      "traffic_unit": "bytes per launch (dram read+write, ncu --set full capture under profiles/)",
                      "launches": int(n_gemm.value), "kernel_ms_per_step": gemm_ms.value / args.steps,
                      "share_of_step": (gemm_ms.value / args.steps) / (ms_total / args.steps),
-                     "peak_source": f"{peaks['source']}: bf16 sustained {peaks['bf16_sustained']} TF/s / 2 (TF32) / 3 (3xTF32) - "
-                                    "fp32-emulated peak; burst would be %.1f.  frac can exceed 1: the sustained figure comes from a cuBLAS bf16 GEMM "
-                                    "that the power cap holds at lower clocks than this kernel runs at" % (peaks["bf16"] / 6.0)},
+                     "peak_source": f"{peaks['source']}: bf16 sustained {peaks['bf16_sustained']} TF/s / 4 (per logical multiply-add: one "
+                                    "TF32 product = 2 bf16-rate units, plus two BF16 correction products) - fp32-emulated peak; "
+                                    "burst would be %.1f" % (peaks["bf16"] / EMU)},
     }
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()

@@ -1,25 +1,30 @@
-// mt_gemm_tc.cu - fp32-accurate GEMM on the Blackwell tensor cores (tcgen05 + TMEM + TMA), 3xTF32.
+// mt_gemm_tc.cu - fp32-accurate GEMM on the Blackwell tensor cores (tcgen05 + TMEM + TMA), split-fp32.
 //
 // Replaces cuBLAS SGEMM behind the reference's `a.data @ b.data`, `grad @ b.T`, `a.T @ grad`
 // (src/tensor/ops/overload.py:132,142,153) as used by Linear (src/nn/layer/linear.py:48).
 //
 //   C[M,N] (+)= act( A'[M,K] . B[K,N] + bias[N] )          fp32 in, fp32 out
 //
-// 3xTF32 split done ON CHIP: x = hi + lo with hi = tf32(x), lo = tf32(x - hi);
-//   A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi   (lo.lo ~ 2^-22 is dropped), fp32 accumulate in TMEM.
-// No split copies ever touch HBM: TMA lands the raw fp32 tile in shared memory - the tensor core truncates it
-// to TF32 itself, so the raw tile IS hi - and four "converter" warps write lo to a second buffer with the SAME
-// (swizzled) layout: the conversion is element-wise on the byte image, so it is independent of the swizzle.
-// The optional backward prologue dZ = dY * (1 - Y^2) is fused into the same pass (the Y tile rides in the raw
-// stage); for large problems the tanh' factor is applied in the PRODUCING GEMM's epilogue instead (epi_tanh).
+// Error-compensated split done ON CHIP: x = hi + lo with hi = trunc_tf32(x), lo = x - hi (exact in fp32);
+//   A.B ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo       (lo.lo ~ 2^-22 is dropped), fp32 accumulate in TMEM.
+// The leading product runs on TF32 from the RAW fp32 tile: TMA lands it in shared memory and the tensor core truncates
+// it to TF32 itself, so the raw tile IS hi.  The two first-order corrections only need ~8 bits of each factor (they are
+// 2^-10 of the result), so they run as BF16 products at twice the TF32 rate: four "converter" warps write
+// bf16(x) and bf16(x - hi) - half the bytes of the fp32 tile each - into a second ring.  Per k-slice of 32: 4 TF32 MMAs
+// (K8) + 4 BF16 MMAs (K16) = 8 tensor slots instead of the 12 of a 3xTF32 split: every GEMM of config #2 is 1.24-1.33x
+// faster, at the same measured accuracy (1e-6 forward, 1.6-1.8e-6 backward; tools/mix_bringup.py, tools/mix_ab.py).
+// mt_gemm_tc_set_mix(0) selects the all-TF32 split (lo rounded to tf32, same layout as the raw tile); the backward
+// prologue variant (dZ = dY * (1 - Y^2) fused into the conversion, small problems only) always uses it.
+// No split copies ever touch HBM.  For large problems the tanh' factor is applied in the PRODUCING GEMM's epilogue
+// (epi_tanh) instead of a prologue.
 //
 // Persistent grid: one CTA PAIR (cluster of 2, tcgen05 cta_group::2) per two SMs loops over 256 x 256 output tiles
 // (single CTAs, 128 x 128 tiles, when N <= 128).  Each CTA = 16 warps in 4 warpgroups:
 //   warp 0      TMA producer      (one lane)            full[r]  <- bytes landed (own A rows, own half of B)
-//   warps 4-7   converters        (128 threads)         conv[l]  <- hi/lo ready, arrives on the LEADER's barrier
+//   warps 4-7   converters        (128 threads)         conv[l]  <- correction tiles ready, arrives on the LEADER's barrier
 //   warp 1      MMA issuer        (leader CTA, 1 lane)  empty[r], lofree[l], tfull[a] <- tcgen05.commit multicast
 //   warps 8-15  accumulate/epilogue (256 threads)       tempty[a] <- accumulator drained (leader's barrier)
-// Two shared-memory rings: a deep raw ring (TMA destination) and a shallow lo ring (converter output).
+// Two shared-memory rings: a deep raw ring (TMA destination) and a shallow correction ring (converter output).
 // The tensor core adds into its fp32 TMEM accumulator with truncation (measured: error grows
 // linearly, ~2^-24 per tcgen05.mma, 7.5e-5 at K=4096), so K is cut into chunks of CHUNK_KB
 // k-blocks: each chunk accumulates into one of two TMEM buffers (ping-pong) and the epilogue
@@ -27,10 +32,11 @@
 // them 200 registers, the data-movement warps 56).  Chunk c+1's MMAs overlap chunk c's drain
 // and the previous tile's bias/tanh/store epilogue.  DESIGN.md section 4.1 has the measurements behind each choice.
 // Operands may be K-major or MN-major (UMMA descriptor transpose bits), so forward (X.W^T), dX
-// (dZ.W) and dW (dZ^T.X) all read the row-major activations/weights in place - no transposes.
+// (dZ.W) and dW (dZ^T.X) all read the row-major activations/weights in place - no transposes; the correction tiles
+// keep the major of their source (K-major: SWIZZLE_64B rows of 32 k; MN-major: SWIZZLE_64B boxes of 32 k x 32 mn).
 //
-// Roofline: tensor pipe (91-99 % active in the ncu captures under profiles/).  One k-block (32) of a 256x256 pair
-// tile is 12 tcgen05.mma (M256 N256 K8), 128 cycles each; logical 2*M*N*K flops are reported against (TF32 peak)/3.
+// Roofline: tensor pipe.  One k-block (32) of a 256x256 pair tile is 4 TF32 + 4 BF16 tcgen05.mma of 128 cycles each;
+// logical 2*M*N*K flops are reported against (bf16 dense peak)/4 = (TF32 peak)/2.
 #include <cuda.h>
 #include <cuda_bf16.h>
 

@@ -321,6 +321,39 @@ def test_linear_ragged_shapes_on_tensor_cores(lib, M, N, K):
     assert gemm_err(dX.get(), (dz @ W) * (1 - X.astype(np.float64) ** 2)) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 512, 768), (640, 1100, 516), (2049, 260, 1028)])
+def test_tensor_core_split_modes_agree(lib, M, N, K):
+    """The default split (hi.hi on TF32, the two first-order corrections as BF16 products) against the all-TF32 split
+    (3xTF32) and float64: forward and both backward GEMMs, every operand-major combination.  Both stay at fp32 level
+    (1e-5 here; the contract is 1e-4), so they also agree with each other to that level."""
+    lib.mt_gemm_tc_set_mix.argtypes = [C.c_int]
+    rng = np.random.default_rng(M + N + K)
+    X = np.tanh(rng.standard_normal((M, K))).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    dZ = rng.standard_normal((M, N)).astype(np.float32)
+    Xd, Wd, bd, dZd = Dev(X), Dev(W), Dev(b), Dev(dZ)
+    Yr = X.astype(np.float64) @ W.astype(np.float64).T + b
+    dWr = dZ.astype(np.float64).T @ X.astype(np.float64)
+    dXr = dZ.astype(np.float64) @ W.astype(np.float64)
+    outs = {}
+    lib.mt_gemm_set_engine(1)
+    try:
+        for mix in (1, 0):
+            lib.mt_gemm_tc_set_mix(mix)
+            Y, dX, dW = Dev(shape=(M, N)), Dev(shape=(M, K)), Dev(shape=(N, K))
+            _capi.check(lib.mt_linear_fwd_f32(Y.ptr, Xd.ptr, Wd.ptr, bd.ptr, M, N, K, 0))
+            _capi.check(lib.mt_linear_bwd_f32(dX.ptr, dW.ptr, dZd.ptr, None, Xd.ptr, Wd.ptr, M, N, K, 0))
+            outs[mix] = (Y.get(), dW.get(), dX.get())
+            for got, ref in zip(outs[mix], (Yr, dWr, dXr)):
+                assert gemm_err(got, ref) < 1e-5
+    finally:
+        lib.mt_gemm_tc_set_mix(1)
+        lib.mt_gemm_set_engine(-1)
+    for a, bb in zip(outs[1], outs[0]):
+        assert gemm_err(a, bb.astype(np.float64)) < 1e-5
+
+
 def test_matmul_generic_strided_and_batched(lib):
     rng = np.random.default_rng(11)
     A = rng.standard_normal((4, 33, 20)).astype(np.float32)

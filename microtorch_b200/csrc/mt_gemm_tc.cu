@@ -21,7 +21,7 @@
 // Persistent grid: one CTA PAIR (cluster of 2, tcgen05 cta_group::2) per two SMs loops over 256 x 256 output tiles
 // (single CTAs, 128 x 128 tiles, when N <= 128).  Each CTA = 16 warps in 4 warpgroups:
 //   warp 0      TMA producer      (one lane)            full[r]  <- bytes landed (own A rows, own half of B)
-//   warps 4-7   converters        (128 threads)         conv[l]  <- correction tiles ready, arrives on the LEADER's barrier
+//   warps 2-7   converters        (192 threads; 4-7 in the all-TF32 mode)  conv[l]  <- correction tiles ready, arrives on the LEADER's barrier
 //   warp 1      MMA issuer        (leader CTA, 1 lane)  empty[r], lofree[l], tfull[a] <- tcgen05.commit multicast
 //   warps 8-15  accumulate/epilogue (256 threads)       tempty[a] <- accumulator drained (leader's barrier)
 // Two shared-memory rings: a deep raw ring (TMA destination) and a shallow correction ring (converter output).
@@ -360,10 +360,11 @@ __device__ __forceinline__ void convert_tile(uint8_t* raw_b, uint8_t* lo_b, int 
 // into bf16(x) and bf16(x - trunc_tf32(x)) and written as two SWIZZLE_64B tiles (64-byte rows; 16-byte chunk q of row r
 // sits at chunk q ^ ((r >> 1) & 3)).  A thread keeps its physical source chunk, so the logical column and the
 // destination offset inside the row are per-thread constants; rows advance by 16 per step.
-template <int VECS>
+template <int VECS, int NTHR>
 __device__ __forceinline__ void convert_tile_mix_k(const uint8_t* raw_b, uint8_t* hi16_b, uint8_t* lo16_b, int ct) {
-  constexpr int PER = VECS / 128;
-  constexpr int U = PER < 4 ? PER : 4;
+  static_assert(NTHR % 64 == 0, "a step must advance whole groups of 8 rows so the swizzle terms stay per-thread constants");
+  constexpr int PER = (VECS + NTHR - 1) / NTHR;                           // float4 per thread (last one may be out of range)
+  constexpr int U = 3;
   const float4* raw = reinterpret_cast<const float4*>(raw_b);
   const int c = (ct & 7) ^ ((ct >> 3) & 7);                               // logical 16-byte chunk: k = 4c .. 4c+3
   const int dst0 = (ct >> 3) * 64 + ((((c >> 1) ^ ((ct >> 4) & 3))) << 4) + ((c & 1) << 3);
@@ -371,20 +372,23 @@ __device__ __forceinline__ void convert_tile_mix_k(const uint8_t* raw_b, uint8_t
   for (int b = 0; b < PER; b += U) {
     float4 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = raw[ct + (b + u) * 128];
+    for (int u = 0; u < U; ++u)
+      if (b + u < PER && ct + (b + u) * NTHR < VECS) v[u] = raw[ct + (b + u) * NTHR];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const float4 x = v[u];
-      float4 lo;
-      lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-      lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-      lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-      lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-      __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
-      const int off = dst0 + (b + u) * 1024;
-      *reinterpret_cast<uint2*>(hi16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-      *reinterpret_cast<uint2*>(lo16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+      if (b + u < PER && ct + (b + u) * NTHR < VECS) {
+        const float4 x = v[u];
+        float4 lo;
+        lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+        lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+        lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+        lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+        __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
+        const int off = dst0 + (b + u) * (NTHR / 8) * 64;
+        *reinterpret_cast<uint2*>(hi16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(lo16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+      }
     }
   }
 }
@@ -394,32 +398,36 @@ __device__ __forceinline__ void convert_tile_mix_k(const uint8_t* raw_b, uint8_t
 // Swizzle<2,4,3> (16-byte chunk q of row k sits at q ^ ((k >> 1) & 3)).  Four consecutive mn are 16 B of the source and
 // 8 B of the destination, and the 32-byte source chunk index equals the 16-byte destination chunk index, so the
 // conversion is element-wise on the byte image again: contiguous loads, contiguous 8-byte stores, no transpose.
-template <int ROWS>
+template <int ROWS, int NTHR>
 __device__ __forceinline__ void convert_tile_mix_mn(const uint8_t* raw_b, uint8_t* hi16_b, uint8_t* lo16_b, int ct) {
-  constexpr int PER = ROWS * 8 / 128;                    // float4 per thread
-  constexpr int U = PER < 4 ? PER : 4;
+  constexpr int VECS = ROWS * 8;
+  constexpr int PER = (VECS + NTHR - 1) / NTHR;          // float4 per thread (last one may be out of range)
+  constexpr int U = 3;
   const float4* raw = reinterpret_cast<const float4*>(raw_b);
 #pragma unroll
   for (int b = 0; b < PER; b += U) {
     float4 v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = raw[ct + (b + u) * 128];
+    for (int u = 0; u < U; ++u)
+      if (b + u < PER && ct + (b + u) * NTHR < VECS) v[u] = raw[ct + (b + u) * NTHR];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = ct + (b + u) * 128;
-      const int box = i >> 8, k = (i & 255) >> 3, p16 = i & 7;
-      const int c32 = (p16 >> 1) ^ (k & 3);
-      const int off = box * 2048 + k * 64 + ((c32 ^ ((k >> 1) & 3)) << 4) + ((p16 & 1) << 3);
-      const float4 x = v[u];
-      float4 lo;
-      lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-      lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-      lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-      lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-      __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
-      *reinterpret_cast<uint2*>(hi16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-      *reinterpret_cast<uint2*>(lo16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+      const int i = ct + (b + u) * NTHR;
+      if (b + u < PER && i < VECS) {
+        const int box = i >> 8, k = (i & 255) >> 3, p16 = i & 7;
+        const int c32 = (p16 >> 1) ^ (k & 3);
+        const int off = box * 2048 + k * 64 + ((c32 ^ ((k >> 1) & 3)) << 4) + ((p16 & 1) << 3);
+        const float4 x = v[u];
+        float4 lo;
+        lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+        lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+        lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+        lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+        __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
+        *reinterpret_cast<uint2*>(hi16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(lo16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+      }
     }
   }
 }
@@ -503,7 +511,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(empty_bar(r), 1);
     }
     for (int l = 0; l < L; ++l) {
-      mbar_init(conv_bar(l), 4 * NCTA);      // converter warps of every CTA of the pair
+      mbar_init(conv_bar(l), ((!PRO && p.mix) ? 6 : 4) * NCTA);   // converter warps of every CTA of the pair
       mbar_init(lofree_bar(l), 1);
     }
     for (int a = 0; a < NUM_ACC; ++a) {
@@ -633,9 +641,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
         }
       }
-    } else if (warp >= 4) {
-      // ===================== converters (warps 4..7, 128 threads) =====================
-      const int ct = threadIdx.x - 128;
+    } else if (warp >= 4 || (!PRO && p.mix)) {
+      // ===================== converters (warps 4..7; in mix mode warps 2..7 = 192 threads) =====================
+      const bool wide = !PRO && p.mix;
+      const int ct = wide ? threadIdx.x - 64 : threadIdx.x - 128;
       int stage = 0, lo = 0;
       uint32_t phase = 0, lphase = 0;
       for (int w = unit; w < num_work; w += num_units) {
@@ -651,10 +660,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             // timing experiment: hand the stage over untouched
           } else {
             if (!PRO && p.mix) {
-              if (A_MN) convert_tile_mix_mn<BM>(sa, sa_lo, sa_lo + C::A_TILE / 2, ct);
-              else convert_tile_mix_k<C::A_TILE / 16>(sa, sa_lo, sa_lo + C::A_TILE / 2, ct);
-              if (B_MN) convert_tile_mix_mn<C::BN_LOCAL>(sb, sb_lo, sb_lo + C::B_TILE / 2, ct);
-              else convert_tile_mix_k<C::B_TILE / 16>(sb, sb_lo, sb_lo + C::B_TILE / 2, ct);
+              if (A_MN) convert_tile_mix_mn<BM, 192>(sa, sa_lo, sa_lo + C::A_TILE / 2, ct);
+              else convert_tile_mix_k<C::A_TILE / 16, 192>(sa, sa_lo, sa_lo + C::A_TILE / 2, ct);
+              if (B_MN) convert_tile_mix_mn<C::BN_LOCAL, 192>(sb, sb_lo, sb_lo + C::B_TILE / 2, ct);
+              else convert_tile_mix_k<C::B_TILE / 16, 192>(sb, sb_lo, sb_lo + C::B_TILE / 2, ct);
             } else {
             if (PRO) convert_tile_prologue<C::A_TILE / 16>(sa, sy, sa_lo, ct);
             else if (p.write_hi) convert_tile<C::A_TILE / 16, true>(sa, sa_lo, ct);

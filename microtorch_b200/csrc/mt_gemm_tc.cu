@@ -11,7 +11,7 @@
 // it to TF32 itself, so the raw tile IS hi.  The two first-order corrections only need ~8 bits of each factor (they are
 // 2^-10 of the result), so they run as BF16 products at twice the TF32 rate: four "converter" warps write
 // bf16(x) and bf16(x - hi) - half the bytes of the fp32 tile each - into a second ring.  Per k-slice of 32: 4 TF32 MMAs
-// (K8) + 4 BF16 MMAs (K16) = 8 tensor slots instead of the 12 of a 3xTF32 split: every GEMM of config #2 is 1.24-1.33x
+// (K8) + 4 BF16 MMAs (K16) = 8 tensor slots instead of the 12 of a 3xTF32 split: the GEMMs of config #2 are 1.18-1.41x
 // faster, at the same measured accuracy (1e-6 forward, 1.6-1.8e-6 backward; tools/mix_bringup.py, tools/mix_ab.py).
 // mt_gemm_tc_set_mix(0) selects the all-TF32 split (lo rounded to tf32, same layout as the raw tile); the backward
 // prologue variant (dZ = dY * (1 - Y^2) fused into the conversion, small problems only) always uses it.

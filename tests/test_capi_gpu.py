@@ -262,7 +262,7 @@ def test_linear_fwd_bwd_small(lib, M, N, K, engine):
 
 def test_tcgen05_engine_is_used_and_accurate(lib):
     """The Linear GEMMs of an MLP-sized layer must run on the tensor cores (engine 1) and match
-    float64 to 1e-4 (3xTF32 keeps ~fp32 accuracy; plain TF32 would be ~1e-3)."""
+    float64 to 1e-4 (the error-compensated split keeps ~fp32 accuracy; plain TF32 would be ~1e-3)."""
     rng = np.random.default_rng(10)
     M, N, K = 1024, 512, 768
     X = rng.standard_normal((M, K)).astype(np.float32)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Where should Linear GEMMs switch from the SIMT fp32 tile to the tcgen05 3xTF32 kernel?  Times mt_linear_fwd_f32 on both
+"""Where should Linear GEMMs switch from the SIMT fp32 tile to the tcgen05 split-fp32 kernel?  Times mt_linear_fwd_f32 on both
 engines over a grid of (M, N, K) and prints one JSON line per shape (run under gpurun).  The dispatch threshold in
 mt_gemm_tc.cu (gemm_tc_try) comes from this table."""
 import ctypes as C

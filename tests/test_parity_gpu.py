@@ -730,6 +730,8 @@ def test_single_launch_trainer_reproduces_the_notebook_and_the_reference(mt):
     (W.scaled(W.C2, 96, (48, 80, 64, 10)), 3),                                # CE with the 0.49*y+0.5 prediction map
     (W.scaled(W.C5, 64, (32,) * 5), 2),                                       # 4 equal layers, MSE
     (W.scaled(W.C2, 37, (5, 7, 3)), 4),                                       # ragged everything
+    (W.scaled(W.C2, 512, (32, 64, 64, 10)), 3),                               # 172 KB of the 227 KB per CTA
+    (W.scaled(W.C5, 96, (24,) * 9), 2),                                       # the maximum depth (8 layers)
 ])
 def test_single_launch_trainer_equals_per_step_path(mt, wl, steps):
     """Same model, same data: one launch for the loop vs one fused-kernel sequence per step (itself checked against

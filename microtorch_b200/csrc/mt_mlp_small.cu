@@ -325,8 +325,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fit_kernel(const __grid_consta
     const bool last = (step == p.steps - 1);
     float* P = sm + p.offP;
     const int total4 = p.offSL >> 2;
+    const int lgc = __ffs((int)csize) - 1;                 // cluster sizes are powers of two
+    // the owner keeps only its own slice of the sums: unit u = rank + C*j lives at P[j]
     for (int u = (int)rank + (int)csize * tid; u < total4; u += (int)csize * nthr)
-      *reinterpret_cast<float4*>(P + 4 * u) = sum_peers4(S + 4 * u, csize);
+      *reinterpret_cast<float4*>(P + 4 * (u >> lgc)) = sum_peers4(S + 4 * u, csize);
     float loss_total = 0.f;
     if (rank == 0 && tid == 0) loss_total = sum_peers(S + p.offSL, csize);
     cluster_sync();
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_fit_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int u = u0 + q * nthr;
-          gs[q] = u < total4 ? ld_peer4(P + 4 * u, (unsigned)u & cmask) : make_float4(0.f, 0.f, 0.f, 0.f);
+          gs[q] = u < total4 ? ld_peer4(P + 4 * (u >> lgc), (unsigned)u & cmask) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -493,7 +495,7 @@ MT_API int mt_mlp_fit_f32(const mt_mlp_desc* desc, const float* X, const float* 
   off = (off + 3) & ~(size_t)3;
   p.offS = (int)off;
   p.offP = (int)(off + sw);
-  off += 2 * sw;
+  off += sw + (size_t)ceil_div((long long)(sw / 4), csize) * 4;      // S in full, P only this rank's 1/C of the units
   const size_t bytes = off * sizeof(float);
   if (bytes > (size_t)SMEM_MAX)
     return fail(MT_ERR_UNSUPPORTED, "mt_mlp_fit_f32: model + batch need %zu bytes of shared memory per CTA (limit %d)", bytes,

@@ -293,7 +293,7 @@ struct Params {
                                // and writes its partial to C + s*M*N (folded by splitk_finalize)
   int raw_stages, lo_stages;   // ring depths (runtime: the split of the 227 KB is a tuning knob)
   int mix;            // 1: corrections as BF16 products from K-major [A_hi16 | A_lo16 | B_hi16 | B_lo16] tiles in the lo ring
-  int dbg;            // timing experiments only (results are wrong): 1 skip the conversion, 2 issue hi*hi only,
+  int dbg;            // timing experiments only (results are wrong): 1 skip the conversion, 8 signal before converting, 2 issue hi*hi only,
                       // 4 issue no MMA at all
 };
 
@@ -656,6 +656,15 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           uint8_t* sy = sb + C::B_TILE;                      // prologue only: Y tile
           uint8_t* sa_lo = smem_gen + R * C::RAW_STAGE + lo * C::LO_STAGE;
           uint8_t* sb_lo = sa_lo + C::A_TILE;
+          if (p.dbg & 8) {
+            // timing experiment (wrong results): signal first, convert afterwards - the MMAs never wait for the
+            // conversion, which still uses the shared-memory port and the issue slots
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(mapa_shared(conv_bar(lo), 0));
+              else mbar_arrive(conv_bar(lo));
+            }
+          }
           if (p.dbg & 1) {
             // timing experiment: hand the stage over untouched
           } else {
@@ -674,7 +683,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
           fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !(p.dbg & 8)) {
             if (PAIR) mbar_arrive_cluster(mapa_shared(conv_bar(lo), 0));      // the LEADER's barrier
             else mbar_arrive(conv_bar(lo));
           }

@@ -16,8 +16,12 @@ gradients are all-reduced with NCCL.  Rank 0 prints ONE JSON line.
              pinned host memory and reads the loss back
   roofline   the dominant kernel (tcgen05 split-fp32 GEMM): logical 2MNK flops / device time measured
              live with CUDA events around every GEMM launch of the timed region
-  cpu_baseline / --impl reference   the oracle port of the reference's NumPy path on the host cores,
-             on a bounded sample (batch 4096) of the same workload
+  cpu_baseline   the oracle port of the reference's NumPy path on the host cores, bounded sample (batch 4096, 3 steps)
+  --impl reference   the same oracle port at the FULL per-GPU batch of the workload (65536 rows, ~11 s per step on 16
+             cores, ~25 GiB of host memory), so both arms run the same config; smaller only if the host lacks the memory
+  dp_parity  (N > 1) before timing: 2 data-parallel steps on a small global batch against a single-process
+             recompute of the same steps on rank 0 - the scaling record carries correctness, not only speed
+  c5         BASELINE config #5 (8 x 4096-wide layers, MSE) at the same rows per GPU, a few steps, as a sub-object
 """
 import argparse
 import ctypes as C
@@ -140,9 +144,23 @@ def cpu_baseline(steps=3, warmup=1):
                       "NumPy elementwise is single-threaded, only matmul uses all cores"}
 
 
+def reference_batch(want):
+    """The per-step batch of the reference arm: the workload's own (65536 rows) when the host has the memory for the
+    oracle's eager zero-filled gradients and temporaries (~25 GiB), else the largest power of two that fits."""
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        avail = 0.0
+    batch = want
+    while batch > CPU_SAMPLE_BATCH and avail < 40.0 * batch / 65536 + 4.0:
+        batch //= 2
+    return batch, avail
+
+
 def run_reference(args, emit):
     """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference
-    is pure Python and cannot travel to the GPU box), bounded sample per step."""
+    is pure Python and cannot travel to the GPU box) at the SAME config as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -150,6 +168,9 @@ def run_reference(args, emit):
     from microtorch_b200 import workloads as W
     from oracle import workloads as OW
     from oracle.nnref import train_step
+    global CPU_SAMPLE_BATCH
+    full = args.batch
+    CPU_SAMPLE_BATCH, avail = reference_batch(full)
     wl = W.scaled(W.C2, CPU_SAMPLE_BATCH)
     model, x, t = OW.setup(wl)
     for _ in range(args.warmup):
@@ -164,16 +185,54 @@ def run_reference(args, emit):
         cores = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
     except Exception:
         cores = os.cpu_count()
-    sample = f"config #2 model, batch {CPU_SAMPLE_BATCH} per step (bounded sample of 65536)"
+    sample = (f"config #2 model, batch {CPU_SAMPLE_BATCH} per step " +
+              ("(the full per-GPU batch: same config as the GPU arm)" if CPU_SAMPLE_BATCH == full else
+               f"(bounded sample of {full}: host memory available {avail:.0f} GiB)"))
     emit({
         "impl": "reference", "metric": "mlp_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c2_mlp_1024_4096_4096_10_tanh_ce_sgd", "per_gpu_batch": 65536, "cpu_sample_batch": CPU_SAMPLE_BATCH},
+        "config": {"workload": "c2_mlp_1024_4096_4096_10_tanh_ce_sgd", "per_gpu_batch": full, "cpu_sample_batch": CPU_SAMPLE_BATCH,
+                   "same_config": CPU_SAMPLE_BATCH == full},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": int(cores), "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
+
+
+def dp_parity_check(comm, dist, rank, world, ns):
+    """Two data-parallel steps of the config #2 model (full widths) on a small global batch (256 rows per rank)
+    against a single-process recompute of the same two steps on rank 0 (same backend, no communicator): norm-wise
+    error of every updated weight and of the global loss.  SURVEY.md 8(e) 'Parity test', tolerance 1e-4."""
+    W, nn, Tanh, Tensor = ns["W"], ns["nn"], ns["Tanh"], ns["Tensor"]
+    from microtorch_b200.nn.loss import CrossEntropyLoss
+    from microtorch_b200.nn.optimizer import SGD
+    from microtorch_b200.trainer import DataParallelTrainer, shard_rows, train_step
+    wl = W.scaled(W.C2, 256 * world)
+    model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)          # same seed everywhere: same replica, same data
+    rows = shard_rows(x.shape[0], rank, world)
+    tr = DataParallelTrainer(model, CrossEntropyLoss(), wl.lr, comm, wl.pred_map, wl.squeeze_dim)
+    Xs, Ts = Tensor(x[rows], device="cuda"), Tensor(t[rows], device="cuda")
+    losses = [tr.global_loss(tr.step(Xs, Ts)) for _ in range(2)]
+    out = None
+    if rank == 0:
+        ref, x2, t2 = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+        Xf, Tf = Tensor(x2, device="cuda"), Tensor(t2, device="cuda")
+        loss_fn, opt = CrossEntropyLoss(), SGD(ref.parameters, lr=wl.lr)
+        ref_losses = [float(train_step(ref, loss_fn, opt, Xf, Tf, wl.pred_map, wl.squeeze_dim).item()) for _ in range(2)]
+        perr = 0.0
+        for a, b in zip(model.parameters(), ref.parameters()):
+            a, b = a.data.get().astype(np.float64), b.data.get().astype(np.float64)
+            perr = max(perr, float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30)))
+        lerr = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
+        out = {"param_err": perr, "loss_err": lerr, "steps": 2, "global_batch": 256 * world, "tolerance": 1e-4,
+               "pass": bool(perr <= 1e-4 and lerr <= 1e-4),
+               # gradients must become final (and their exchange start) last layer first, during the backward pass
+               "exchange_order_last_layer_first":
+               tr.hook_order == [id(p) for p in reversed(list(model.parameters())[0::2])],
+               "against": "single-process recompute of the same steps on rank 0 (device path, no communicator)"}
+    dist.barrier()
+    return out
 
 
 def main():
@@ -185,6 +244,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
     ap.add_argument("--batch", type=int, default=65536, help="rows per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the config #5 sub-object")
     args = ap.parse_args()
     # stdout carries exactly ONE line - the JSON result.  Libraries write banners to fd 1 (NCCL prints its version
     # there when NCCL_DEBUG asks for it), so everything else is sent to stderr for the duration of the run.
@@ -241,6 +301,9 @@ def main():
             dist.broadcast_object_list(box, src=0)
             return box[0]
         comm = Communicator(rank, world, exchange)
+    dp_parity = None
+    if world > 1:
+        dp_parity = dp_parity_check(comm, dist, rank, world, {"W": W, "nn": nn, "Tanh": Tanh, "Tensor": Tensor})
     loss_fn = CrossEntropyLoss() if wl.loss == "ce" else MSELoss()
     trainer = DataParallelTrainer(model, loss_fn, wl.lr, comm, wl.pred_map, wl.squeeze_dim)
 
@@ -322,9 +385,38 @@ def main():
         e2e_loss.append(loss.item())
 
     step_e2e()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = args.steps          # the same number of steps as `value` (under the power cap 10 vs 20 steps differ)
     ms_e2e = timed(step_e2e, e2e_steps)
     e2e_value = args.batch * world * e2e_steps / (ms_e2e / 1e3)
+
+    # ------------------------------------------------------------- BASELINE config #5 (the named data-parallel config)
+    c5 = None
+    if args.workload == "c2" and not args.no_c5:
+        X = T = px = pt = trainer = model = None      # release config #2 (closures above keep only the names)
+        pending.clear()
+        last.clear()
+        lib.mt_pool_trim()
+        wl5 = W.scaled(W.C5, args.batch)
+        np.random.seed(wl5.seed)
+        model5 = W.build_model(wl5, nn.Linear, Tanh, nn.Sequential)
+        rng5 = np.random.default_rng(2000 + rank)
+        X5 = Tensor(rng5.standard_normal((args.batch, wl5.dims[0]), dtype=np.float32), device="cuda")
+        T5 = Tensor(rng5.uniform(-1, 1, (args.batch, wl5.dims[-1])).astype(np.float32), device="cuda")
+        tr5 = DataParallelTrainer(model5, MSELoss(), wl5.lr, comm, wl5.pred_map, wl5.squeeze_dim)
+        for _ in range(3):
+            last["loss"] = tr5.step(X5, T5)
+        c5_steps = max(3, min(args.steps, 5))
+        lib.mt_prof_reset()
+        lib.mt_prof_enable(1)
+        ms5 = timed(lambda: last.__setitem__("loss", tr5.step(X5, T5)), c5_steps)
+        n5, gms5, gfl5 = C.c_uint64(), C.c_double(), C.c_double()
+        lib.mt_prof_gemm(C.byref(n5), C.byref(gms5), C.byref(gfl5))
+        lib.mt_prof_enable(0)
+        c5 = {"workload": "c5_mlp_4096x8_tanh_mse_sgd", "per_gpu_batch": args.batch, "global_batch": args.batch * world,
+              "value": args.batch * world * c5_steps / (ms5 / 1e3), "unit": "samples/s", "ms_per_step": ms5 / c5_steps,
+              "steps": c5_steps, "warmup": 3, "loss": tr5.global_loss(last["loss"]),
+              "gemm_tflops_logical_per_gpu": (gfl5.value / (gms5.value * 1e-3) / 1e12) if gms5.value else None,
+              "step_tflops_logical_per_gpu": wl5.gemm_flops_per_step(args.batch) / (ms5 / c5_steps * 1e-3) / 1e12}
 
     if rank != 0:
         if dist is not None:
@@ -351,7 +443,7 @@ def main():
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
         "gpu_launches": int(launches.value),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm3xtf32_kernel (tcgen05)", "achieved": achieved_tf, "peak": peak_tf,
+        "roofline": {"bound": "tensor", "kernel": "gemm_splitfp32_kernel (tcgen05)", "achieved": achieved_tf, "peak": peak_tf,
                      "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None,
                      "frac_of_burst_peak": achieved_tf / (peaks["bf16"] / EMU) if peaks["bf16"] else None,
                      "traffic": ncu_traffic_per_launch(),
@@ -362,6 +454,10 @@ def main():
                                     "TF32 product = 2 bf16-rate units, plus two BF16 correction products) - fp32-emulated peak; "
                                     "burst would be %.1f" % (peaks["bf16"] / EMU)},
     }
+    if dp_parity is not None:
+        out["dp_parity"] = dp_parity
+    if c5 is not None:
+        out["c5"] = c5
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     emit(out)

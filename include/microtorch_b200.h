@@ -191,7 +191,12 @@ typedef enum mt_act { MT_ACT_NONE = 0, MT_ACT_TANH = 1 } mt_act;
 /* Y[M,N] = act( X[M,K] . W[N,K]^T + bias[N] )      X, W, Y row-major, contiguous
  * replaces: Linear.forward = (W @ x^T)^T, `output += bias` and the following Tanh
  * (src/nn/layer/linear.py:48-62, src/nn/activation.py:11-12, overload.py:132).
- * tcgen05/TMEM 3xTF32 tiles fed by TMA; bias add + tanh fused in the epilogue.          */
+ * tcgen05/TMEM tiles fed by TMA, fp32 kept by an error-compensated split done on chip:
+ *   x = hi + lo, hi = trunc_tf32(x);  A.B ~= A_hi.B_hi (TF32) + A_lo.B_hi + A_hi.B_lo (both as BF16 products,
+ *   8 bits are enough for terms that are 2^-10 of the result; lo.lo ~ 2^-22 dropped), fp32 accumulation folded
+ *   every K=256 into IEEE running sums.  This is the north_star's "3xTF32 split" with the two correction
+ *   products moved to BF16: same measured accuracy (1e-6 forward, < 2e-6 backward), 1.2-1.4x faster;
+ *   mt_gemm_tc_set_mix(0) selects the literal all-TF32 split.  bias add + tanh fused in the epilogue.     */
 int mt_linear_fwd_f32(float* Y, const float* X, const float* W, const float* bias_or_null,
                       int64_t M, int64_t N, int64_t K, int act);
 /* dZ = dY * (1 - Yact^2) if Yact != NULL else dY          (tanh' fused in the prologue)
@@ -272,8 +277,26 @@ int mt_comm_world(int* rank, int* world);
 /* sum-allreduce `n` floats in place on the communication stream; ordered after all work
  * already queued on the compute stream.  mt_comm_wait() makes the compute stream wait.  */
 int mt_allreduce_sum_f32(float* buf, size_t n);
+/* all-reduce `grad`, then  param -= lr * grad  (reference: src/nn/optimizer.py:37-39), both on the communication
+ * stream: the update of layer L runs under the backward GEMMs of the layers below it.  When `grad` is the dW that
+ * the last mt_linear_bwd_f32 produced the exchange starts as soon as that GEMM is done (not after the dX GEMM queued
+ * behind it); the update itself is ordered after everything queued on the compute stream at the time of the call.
+ * Without a communicator (world 1) it is just the deferred update.  Readers of `param` must follow mt_comm_wait(). */
+int mt_allreduce_sgd_f32(float* param, float* grad, size_t n, float lr);
+/* make the compute stream wait for the communication stream; also polls ncclCommGetAsyncError (a dead peer aborts
+ * the communicator and returns MT_ERR_NCCL instead of hanging)                                                   */
 int mt_comm_wait(void);
+int mt_comm_check(void);
 int mt_comm_destroy(void);
+
+/* ---------------------------------------------------------------- timeline -------- */
+/* A device-side timeline without a profiler: while enabled, every kernel launch is followed by a timed CUDA event on
+ * its stream (stream_id 0 = compute, 1 = communication).  Entry i is (label, stream, ms since entry 0); on one
+ * stream consecutive entries bracket one kernel.  tools/dp_timeline.py turns it into profiles/r02_dp_timeline_*.  */
+int mt_trace_enable(int on);
+int mt_trace_reset(void);
+int mt_trace_count(int* n);
+int mt_trace_get(int i, char* label, size_t label_cap, int* stream_id, float* ms_since_first);
 
 #ifdef __cplusplus
 }

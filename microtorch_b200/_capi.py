@@ -98,8 +98,14 @@ PROTOTYPES = {
     "mt_comm_init_rank": [C.c_char_p, C.c_int, C.c_int],
     "mt_comm_world": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "mt_allreduce_sum_f32": [VP, C.c_size_t],
+    "mt_allreduce_sgd_f32": [VP, VP, C.c_size_t, C.c_float],
     "mt_comm_wait": [],
+    "mt_comm_check": [],
     "mt_comm_destroy": [],
+    "mt_trace_enable": [C.c_int],
+    "mt_trace_reset": [],
+    "mt_trace_count": [C.POINTER(C.c_int)],
+    "mt_trace_get": [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_float)],
 }
 # return `const char*`
 STRING_FUNCS = ("mt_last_error", "mt_version")

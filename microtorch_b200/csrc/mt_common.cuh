@@ -34,6 +34,11 @@ struct Global {
   int gemm_last_engine = -1;
   void* l2_flush_buf = nullptr;
   size_t l2_flush_bytes = 0;
+  bool trace_on = false;               // mt_trace_*: one timed event per launch (a device-side timeline)
+  // the dW of the last mt_linear_bwd_f32: an all-reduce of exactly this buffer may start as soon as dW is done,
+  // without waiting for the dX GEMM queued behind it
+  const void* dw_ready_ptr = nullptr;
+  cudaEvent_t ev_dw_ready = nullptr;
 };
 Global& g();
 
@@ -59,10 +64,14 @@ int fail(int status, const char* fmt, ...);
     if (!(cond)) return mt::fail(MT_ERR_INVALID, __VA_ARGS__);                       \
   } while (0)
 
+// timeline tracing (mt_trace_*): a timed event on `stream` labelled `name` (a string literal)
+void trace_mark(const char* name, cudaStream_t stream, int stream_id);
+
 // to be called right after a <<<>>> launch
 #define MT_LAUNCHED()                                                                \
   do {                                                                               \
     mt::g().launches++;                                                              \
+    if (mt::g().trace_on) mt::trace_mark(__func__, mt::g().stream, 0);               \
     cudaError_t e__ = cudaGetLastError();                                            \
     if (e__ != cudaSuccess)                                                          \
       return mt::fail(MT_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,  \
@@ -72,6 +81,7 @@ int fail(int status, const char* fmt, ...);
 // pool (mt_pool.cu)
 int pool_alloc(void** p, size_t bytes);
 int pool_free(void* p);
+void pool_mark_foreign(const void* p, int stream_bit);   // 1: copy stream, 2: communication stream
 
 // Scratch block from the pool, returned on every exit path (pool_free is stream-ordered, so handing the block back
 // right after the kernels that use it were queued is safe).

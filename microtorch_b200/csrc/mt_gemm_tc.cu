@@ -108,6 +108,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// same with an L2 eviction-priority hint (createpolicy encodings: 0x12F0.. evict_first, 0x14F0.. evict_last)
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                 uint64_t policy) {
+  if (policy == 0) { tma_load_2d(dst, map, bar, c0, c1); return; }
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -292,6 +301,9 @@ struct Params {
   int splits, kb_per_split;    // split-K: work item = (tile, split); split s covers k-blocks [s*kbps, (s+1)*kbps)
                                // and writes its partial to C + s*M*N (folded by splitk_finalize)
   int raw_stages, lo_stages;   // ring depths (runtime: the split of the 227 KB is a tuning knob)
+  int group_n;        // tile order: n-blocks per column group (see work_decode)
+  unsigned long long hint_a, hint_b;   // L2 eviction-priority policies of the A / B tile loads (0 = none)
+  int store_cs;       // epilogue stores C with st.global.cs (streaming: the output is not re-read by this kernel)
   int mix;            // 1: corrections as BF16 products from K-major [A_hi16 | A_lo16 | B_hi16 | B_lo16] tiles in the lo ring
   int dbg;            // timing experiments only (results are wrong): 1 skip the conversion, 8 signal before converting, 2 issue hi*hi only,
                       // 4 issue no MMA at all
@@ -474,7 +486,7 @@ __device__ __forceinline__ void convert_tile_prologue(uint8_t* raw_b, const uint
 //   (remote mbarrier arrive), MMA -> both CTAs' empty[s] / tfull[a] (multicast commit), epilogues -> leader's tempty[a].
 template <int BN, bool A_MN, bool B_MN, int NCTA, bool PRO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+gemm_splitfp32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ CUtensorMap map_t, const Params p) {
   using C = Cfg<BN, NCTA, PRO>;
   constexpr int MS = C::MAX_STAGES;
@@ -526,12 +538,30 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int num_work = p.m_blocks * p.n_blocks * p.splits;   // (tile of (128*NCTA) x BN, k-split) pairs
+  const int num_tiles = p.m_blocks * p.n_blocks;
+  const int num_work = num_tiles * p.splits;   // (tile of (128*NCTA) x BN, k-split) pairs
   const int chunk_kb = p.chunk_kb;
-  // work item w -> tile index, k-block range
-  auto work_tile = [&](int w) { return w / p.splits; };
-  auto work_kb0 = [&](int w) { return (w % p.splits) * p.kb_per_split; };
-  auto work_kb1 = [&](int w) { return min(((w % p.splits) + 1) * p.kb_per_split, p.k_blocks); };
+  // Work item w -> (k-split, m-block, n-block).  The units take items round-robin, so the items [i*U, (i+1)*U) run at the
+  // same time ("a wave") and should share operand panels in L2:
+  //   * the k-split is the SLOWEST index: a wave reads one K range, so all its tiles walk K in step and every A / B
+  //     k-slice is fetched from HBM once and shared through L2 by the tiles of its row / column;
+  //   * inside a split the n-blocks are cut into column groups of `group_n`; a group is walked m-block by m-block
+  //     with its n-blocks fastest.  A wave is then a (U / group_n) x group_n rectangle of tiles - it touches
+  //     U/group_n + group_n operand panels instead of U/n_blocks + n_blocks - and the group's B panels stay hot in L2
+  //     from wave to wave while A streams through once per group.
+  // group_n == n_blocks is the plain row-major order.
+  const int group_items = p.m_blocks * p.group_n;
+  auto work_split = [&](int w) { return w / num_tiles; };
+  auto work_mn = [&](int w, int& mb, int& nb) {
+    const int t = w % num_tiles;
+    const int grp = t / group_items;
+    const int r = t - grp * group_items;
+    const int width = min(p.group_n, p.n_blocks - grp * p.group_n);
+    mb = r / width;
+    nb = grp * p.group_n + (r - mb * width);
+  };
+  auto work_kb0 = [&](int w) { return work_split(w) * p.kb_per_split; };
+  auto work_kb1 = [&](int w) { return min((work_split(w) + 1) * p.kb_per_split, p.k_blocks); };
 
   if (warp < 8) {
     reg_dec<REGS_MOVERS>();
@@ -542,9 +572,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         uint32_t phase = 0;
         const uint32_t tx_bytes = C::RAW_STAGE;
         for (int w = unit; w < num_work; w += num_units) {
-          const int tile = work_tile(w);
-          const int m0 = (tile / p.n_blocks) * (BM * NCTA) + int(cta_rank) * BM;
-          const int n0 = (tile % p.n_blocks) * BN + int(cta_rank) * C::BN_LOCAL;
+          int mb, nb;
+          work_mn(w, mb, nb);
+          const int m0 = mb * (BM * NCTA) + int(cta_rank) * BM;
+          const int n0 = nb * BN + int(cta_rank) * C::BN_LOCAL;
           for (int kb = work_kb0(w), kbe = work_kb1(w); kb < kbe; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1, 0);
             const uint32_t sa = smem_base + stage * C::RAW_STAGE;
@@ -556,18 +587,18 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (A_MN) {
 #pragma unroll
               for (int j = 0; j < BM / 32; ++j) {   // 32(m) x 32(k) boxes, 4096 B each
-                tma_load_2d(sa + j * 4096, &map_a, fb, m0 + j * 32, k0);
+                tma_load_2d_hint(sa + j * 4096, &map_a, fb, m0 + j * 32, k0, p.hint_a);
                 if (PRO) tma_load_2d(sa_lo + j * 4096, &map_t, fb, m0 + j * 32, k0);
               }
             } else {
-              tma_load_2d(sa, &map_a, fb, k0, m0);    // 32(k) x 128(m) box
+              tma_load_2d_hint(sa, &map_a, fb, k0, m0, p.hint_a);    // 32(k) x 128(m) box
               if (PRO) tma_load_2d(sa_lo, &map_t, fb, k0, m0);
             }
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < C::BN_LOCAL / 32; ++j) tma_load_2d(sb + j * 4096, &map_b, fb, n0 + j * 32, k0);
+              for (int j = 0; j < C::BN_LOCAL / 32; ++j) tma_load_2d_hint(sb + j * 4096, &map_b, fb, n0 + j * 32, k0, p.hint_b);
             } else {
-              tma_load_2d(sb, &map_b, fb, k0, n0);
+              tma_load_2d_hint(sb, &map_b, fb, k0, n0, p.hint_b);
             }
             if (++stage == R) { stage = 0; phase ^= 1; }
           }
@@ -702,9 +733,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     float run[COLS];
     uint32_t cc = 0;
     for (int w = unit; w < num_work; w += num_units) {
-      const int tile = work_tile(w);
-      const long long m0 = (long long)(tile / p.n_blocks) * (BM * NCTA) + (long long)cta_rank * BM;
-      const long long n0 = (long long)(tile % p.n_blocks) * BN;
+      int mb, nb;
+      work_mn(w, mb, nb);
+      const long long m0 = (long long)mb * (BM * NCTA) + (long long)cta_rank * BM;
+      const long long n0 = (long long)nb * BN;
       const int kb_begin = work_kb0(w), kb_end = work_kb1(w);
       for (int kb0 = kb_begin; kb0 < kb_end; kb0 += chunk_kb, ++cc) {
         const int acc = cc & 1;
@@ -734,7 +766,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       // ---- tile epilogue: bias, tanh, (accumulate), store.  One row per thread, 128 B per 32 columns.
       const long long row = m0 + quad * 32 + lane;
       if (row < p.M) {
-        float* crow = p.C + (long long)(w % p.splits) * p.M * p.N + row * p.N;   // split partials are stacked
+        float* crow = p.C + (long long)work_split(w) * p.M * p.N + row * p.N;   // split partials are stacked
         const long long nb0 = n0 + half * COLS;
 #pragma unroll
         for (int j = 0; j < COLS; j += 4) {
@@ -755,7 +787,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             float4* dst = reinterpret_cast<float4*>(crow + n);
             if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            *dst = v;
+            if (p.store_cs) __stcs(dst, v);
+            else *dst = v;
           }
         }
       }
@@ -839,6 +872,9 @@ static int g_splitk = 1;      // allow split-K for badly quantised tile counts
 static int g_lo_stages = 3;   // lo ring depth; the raw ring gets whatever else fits (or g_raw_stages if > 0)
 static int g_raw_stages = 0;
 static int g_mix = 1;         // 1 (default): hi.hi on TF32, the two first-order corrections as BF16 products; 0: 3xTF32
+static int g_group_n = 0;     // tile order: 0 = choose per problem (see launch), > 0 = that many n-blocks per column group,
+                              // < 0 = plain row-major order (all n-blocks in one group)
+static int g_hints = 3;       // bit 0: L2 eviction-priority hints on the operand loads, bit 1: streaming C stores
 static int g_pair = 1;        // 1: CTA pairs (cta_group::2) for N > 128 when the shape allows; 0: single CTAs only
 
 template <int BN, bool A_MN, bool B_MN, int NCTA, bool PRO>
@@ -882,7 +918,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
     const int fit = (room - l * C::LO_STAGE) / C::RAW_STAGE;
     if (r <= 0 || r > fit) r = fit;
     if (r > C::MAX_STAGES) r = C::MAX_STAGES;
-    if (r < 1) return fail(MT_ERR_INVALID, "gemm3xtf32: no room for a raw stage");
+    if (r < 1) return fail(MT_ERR_INVALID, "gemm_splitfp32: no room for a raw stage");
     p.raw_stages = r;
     p.lo_stages = l;
   }
@@ -908,6 +944,31 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   }
   p.kb_per_split = (int)ceil_div(p.k_blocks, S);
   p.splits = (int)ceil_div(p.k_blocks, p.kb_per_split);
+  {
+    // Tile order (work_mn in the kernel).  A B panel is BN rows x this split's K.  If ALL of B's panels fit in a third
+    // of L2 the plain order is best: B stays resident, A and C stream through exactly once.  Otherwise cut the n-blocks
+    // into column groups about sqrt(units) wide: a wave of U concurrent tiles then touches ~2*sqrt(U) panels instead of
+    // n_blocks + U/n_blocks, the group's B panels are what stays hot in L2, and A is re-read once per group.
+    const double b_panel = (double)BN * (double)p.kb_per_split * BK * 4.0;
+    int gn = p.n_blocks;
+    if (g_group_n > 0) gn = std::min(g_group_n, p.n_blocks);
+    else if (g_group_n == 0 && p.n_blocks * b_panel > (double)g().l2_bytes / 3.0) {
+      int root = 1;
+      while ((long long)(root + 1) * (root + 1) <= unit_count) ++root;         // floor(sqrt(units)): 8 for 74 pairs
+      const int groups = (int)ceil_div(p.n_blocks, root);
+      gn = (int)ceil_div(p.n_blocks, groups);                                   // equal-width groups
+    }
+    p.group_n = gn < 1 ? 1 : gn;
+    // L2 priorities: the B panels of the current column group are re-read by every wave -> evict_last; A is read by the
+    // group_n concurrent tiles of its row and then not again before a whole group has gone by -> evict_first.  When K is
+    // so long that not even one group of B panels fits (dW: K = batch rows), nothing is reused across waves: no hints.
+    const bool b_reused = p.group_n * b_panel <= (double)g().l2_bytes / 2.0 && p.m_blocks * p.group_n > unit_count;
+    p.hint_a = ((g_hints & 1) && b_reused) ? 0x12F0000000000000ull : 0ull;
+    p.hint_b = ((g_hints & 1) && b_reused) ? 0x14F0000000000000ull : 0ull;
+    // C streams out (evict-first) when it is far larger than L2 and nobody re-reads it soon (split-K partials are folded
+    // right away: they keep the default policy)
+    p.store_cs = ((g_hints & 2) && p.splits == 1 && (double)a.M * a.N * 4.0 > (double)g().l2_bytes / 2.0) ? 1 : 0;
+  }
   PoolScratch scratch;
   float* partial = nullptr;
   if (p.splits > 1) {
@@ -923,7 +984,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   const int smem_bytes = C::smem_bytes(p.raw_stages, p.lo_stages);
   rc = ensure_debug_word();
   if (rc) return rc;
-  auto kern = gemm3xtf32_kernel<BN, A_MN, B_MN, NCTA, PRO>;
+  auto kern = gemm_splitfp32_kernel<BN, A_MN, B_MN, NCTA, PRO>;
   static bool attr_set = false;
   if (!attr_set) {
     MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_MAX));
@@ -954,8 +1015,13 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
     cudaEventRecord(rec.b, g().stream);
     g_prof.push_back(rec);
   }
-  if (le != cudaSuccess) return fail(MT_ERR_CUDA, "gemm3xtf32 launch failed: %s", cudaGetErrorString(le));
-  MT_LAUNCHED();
+  if (le != cudaSuccess) return fail(MT_ERR_CUDA, "gemm_splitfp32 launch failed: %s", cudaGetErrorString(le));
+  g().launches++;
+  if (g().trace_on) {
+    char label[56];
+    snprintf(label, sizeof(label), "tc_gemm %lldx%lldx%lld %c%c s%d", a.M, a.N, a.K, A_MN ? 'm' : 'k', B_MN ? 'm' : 'k', p.splits);
+    trace_mark(label, g().stream, 0);
+  }
   if (partial) {
     rc = splitk_finalize(a.C, partial, p.splits, a.M, a.N, a.bias, a.act, a.accumulate, a.epi_tanh);
     if (rc) return rc;
@@ -1066,6 +1132,16 @@ extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_splitk(int 
 }
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_dbg(int v) {
   tc::g_dbg_flags = v;
+  return MT_OK;
+}
+//   group_n  : tile order - 0 (default) chosen per problem, n > 0 that many n-blocks per column group, < 0 row-major.
+//   hints    : bit 0 = L2 eviction-priority hints on operand loads, bit 1 = streaming stores of C (default 3).
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_group_n(int v) {
+  tc::g_group_n = v;
+  return MT_OK;
+}
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_hints(int v) {
+  tc::g_hints = v;
   return MT_OK;
 }
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_pair(int v) {

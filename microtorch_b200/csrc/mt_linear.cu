@@ -117,6 +117,11 @@ MT_API int mt_linear_bwd_f32(float* dX, float* dW, const float* dY, const float*
     a.b_sk = K; a.b_sn = 1;     // B(k'=row, n'=k) = X[row, k]
     a.accumulate = accumulate_dW;
     rc = attempt(a);
+    if (rc == MT_OK) {   // dW is complete here: a gradient exchange of it need not wait for the dX GEMM below
+      Global& G = g();
+      if (cudaEventRecord(G.ev_dw_ready, G.stream) == cudaSuccess) G.dw_ready_ptr = dW;
+      else { cudaGetLastError(); G.dw_ready_ptr = nullptr; }
+    }
   }
   if (rc == MT_OK && dX) {  // dX[M,K] = dZ . W    GEMM  M'=M, N'=K, K'=N
     GemmArgs a{};

@@ -24,12 +24,12 @@ template <int KIND, bool WRITE_GRAD>
 __global__ void __launch_bounds__(THREADS) loss_kernel(float* __restrict__ loss_out, float* __restrict__ dpred,
                                                        const float* __restrict__ pred, const float* __restrict__ target,
                                                        size_t n, float scale, float* __restrict__ partials,
-                                                       unsigned int* __restrict__ ticket) {
+                                                       unsigned int* __restrict__ ticket, int vec) {
   __shared__ float smem[THREADS / 32];
   __shared__ bool is_last;
   const size_t tid = (size_t)blockIdx.x * THREADS + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * THREADS;
-  const size_t n4 = n >> 2;
+  const size_t n4 = vec ? (n >> 2) : 0;   // a mis-aligned view (an odd-offset slice) takes the scalar loop for everything
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   size_t i = tid;
   for (; i + stride < n4; i += 2 * stride) {  // two independent vector pairs in flight
@@ -102,6 +102,7 @@ struct SgdTable {
   float* g[CAP];
   unsigned long long start4[CAP + 1];  // prefix of float4 counts
   unsigned long long n[CAP];           // element counts
+  unsigned char vec[CAP];              // both pointers 16 B aligned -> 128-bit accesses
 };
 
 template <bool ZERO>
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(THREADS) sgd_multi_kernel(const __grid_constan
     float* __restrict__ pp = t.p[cur];
     float* __restrict__ gg = t.g[cur];
     const unsigned long long n = t.n[cur];
-    if (4 * k + 3 < n) {
+    if (4 * k + 3 < n && t.vec[cur]) {
       float4 pv = *reinterpret_cast<float4*>(pp + 4 * k);
       float4 gv = *reinterpret_cast<const float4*>(gg + 4 * k);
       // p + (-(lr*g)): two roundings, exactly as NumPy does it (no FMA contraction)
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(THREADS) sgd_multi_kernel(const __grid_constan
       *reinterpret_cast<float4*>(pp + 4 * k) = pv;
       if (ZERO) *reinterpret_cast<float4*>(gg + 4 * k) = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
-      for (unsigned long long j = 4 * k; j < n; ++j) {
+      const unsigned long long je = (4 * k + 4 < n) ? 4 * k + 4 : n;   // ragged tail or a mis-aligned view
+      for (unsigned long long j = 4 * k; j < je; ++j) {
         pp[j] = __fsub_rn(pp[j], __fmul_rn(lr, gg[j]));
         if (ZERO) gg[j] = 0.f;
       }
@@ -141,8 +143,10 @@ MT_API int mt_loss_fwd_bwd_f32(int kind, float* loss_out, float* dpred, const fl
   MT_REQUIRE_INIT();
   MT_CHECK_ARG(loss_out && pred && target, "mt_loss_fwd_bwd_f32: null pointer");
   MT_CHECK_ARG(n > 0, "mt_loss_fwd_bwd_f32: empty input");
-  MT_CHECK_ARG(((uintptr_t)pred & 15) == 0 && ((uintptr_t)target & 15) == 0 && ((uintptr_t)dpred & 15) == 0,
-               "mt_loss_fwd_bwd_f32: operands must be 16 B aligned (dense pool blocks)");
+  MT_CHECK_ARG(((uintptr_t)pred & 3) == 0 && ((uintptr_t)target & 3) == 0 && ((uintptr_t)dpred & 3) == 0,
+               "mt_loss_fwd_bwd_f32: operands must be float aligned");
+  // basic-slice views (X[i:i+b]) start anywhere: 128-bit accesses only when all three operands allow them
+  const int vec = (((uintptr_t)pred | (uintptr_t)target | (uintptr_t)dpred) & 15) == 0;
   LossScratch& S = scratch();
   const int grid = ew_grid((int64_t)(n / 4 + 1), THREADS * 2);
   if (S.cap < grid) {
@@ -161,8 +165,8 @@ MT_API int mt_loss_fwd_bwd_f32(int kind, float* loss_out, float* dpred, const fl
   cudaStream_t st = g().stream;
 #define MT_LOSS(K)                                                                                              \
   do {                                                                                                          \
-    if (dpred) loss_kernel<K, true><<<grid, THREADS, 0, st>>>(loss_out, dpred, pred, target, n, scale, S.partials, S.ticket); \
-    else loss_kernel<K, false><<<grid, THREADS, 0, st>>>(loss_out, dpred, pred, target, n, scale, S.partials, S.ticket);      \
+    if (dpred) loss_kernel<K, true><<<grid, THREADS, 0, st>>>(loss_out, dpred, pred, target, n, scale, S.partials, S.ticket, vec); \
+    else loss_kernel<K, false><<<grid, THREADS, 0, st>>>(loss_out, dpred, pred, target, n, scale, S.partials, S.ticket, vec); \
   } while (0)
   switch (kind) {
     case MT_LOSS_MSE: MT_LOSS(MT_LOSS_MSE); break;
@@ -187,8 +191,9 @@ MT_API int mt_sgd_multi_f32(float* const* params, float* const* grads, const siz
     while (done < count && k < SgdTable::CAP) {
       if (sizes[done]) {
         MT_CHECK_ARG(params[done] && grads[done], "mt_sgd_multi_f32: null tensor %d", done);
-        MT_CHECK_ARG(((uintptr_t)params[done] & 15) == 0 && ((uintptr_t)grads[done] & 15) == 0,
-                     "mt_sgd_multi_f32: tensor %d not 16 B aligned", done);
+        MT_CHECK_ARG(((uintptr_t)params[done] & 3) == 0 && ((uintptr_t)grads[done] & 3) == 0,
+                     "mt_sgd_multi_f32: tensor %d not float aligned", done);
+        t.vec[k] = (((uintptr_t)params[done] | (uintptr_t)grads[done]) & 15) == 0;
         t.p[k] = params[done];
         t.g[k] = grads[done];
         t.n[k] = sizes[done];

@@ -29,6 +29,28 @@ int fail(int status, const char* fmt, ...) {
   return status;
 }
 
+// ------------------------------------------------------------------ timeline tracing
+// nsys is not available on the pool, so the library can draw its own timeline: while tracing is on, every kernel
+// launch is followed by a timed CUDA event on its stream (compute launches via MT_LAUNCHED, collectives and the
+// per-parameter updates of the communication stream explicitly).  On one stream consecutive events bracket one
+// kernel, so the dump is a per-stream Gantt chart of a training step (tools/dp_timeline.py).
+struct TraceRec { cudaEvent_t ev; char name[56]; int stream_id; };
+static std::vector<TraceRec> g_trace;
+static std::vector<cudaEvent_t> g_trace_pool;
+
+void trace_mark(const char* name, cudaStream_t stream, int stream_id) {
+  cudaEvent_t e;
+  if (!g_trace_pool.empty()) { e = g_trace_pool.back(); g_trace_pool.pop_back(); }
+  else if (cudaEventCreate(&e) != cudaSuccess) return;
+  if (cudaEventRecord(e, stream) != cudaSuccess) { cudaGetLastError(); g_trace_pool.push_back(e); return; }
+  TraceRec r;
+  r.ev = e;
+  r.stream_id = stream_id;
+  strncpy(r.name, name, sizeof(r.name) - 1);
+  r.name[sizeof(r.name) - 1] = 0;
+  g_trace.push_back(r);
+}
+
 // ------------------------------------------------------------------ caching pool
 // Size-class free lists.  All library work is ordered on one compute stream, so a block
 // returned by mt_free can be handed out again immediately: any kernel still reading it was
@@ -39,6 +61,7 @@ struct Block {
   size_t size = 0;
   int graph = 0;       // 0: ordinary block; g > 0: allocated while graph g was being captured
   bool held = true;    // the caller still owns it (not yet passed to mt_free)
+  int foreign = 0;     // streams other than the compute stream that were given work on it: 1 copy, 2 communication
 };
 struct Pool {
   std::mutex mu;
@@ -117,14 +140,40 @@ int pool_alloc(void** out, size_t bytes) {
   return MT_OK;
 }
 
+// A prefetch (copy stream) or a collective / deferred update (communication stream) was queued on the block that
+// contains `p`.  Reuse of a freed block is only ordered on the compute stream, so pool_free makes the compute stream
+// wait for those streams before the block can be handed out again.
+void pool_mark_foreign(const void* p, int stream_bit) {
+  if (!p) return;
+  Pool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  auto it = P.blocks.upper_bound(const_cast<void*>(p));
+  if (it == P.blocks.begin()) return;
+  --it;
+  if ((const char*)p < (const char*)it->first + it->second.size) it->second.foreign |= stream_bit;
+}
+
 int pool_free(void* p) {
   if (!p) return MT_OK;
+  if (p == g().dw_ready_ptr) g().dw_ready_ptr = nullptr;   // the pointer may come back as somebody else's buffer
   Pool& P = pool();
   std::lock_guard<std::mutex> lk(P.mu);
   auto it = P.blocks.find(p);
   if (it == P.blocks.end() || !it->second.held)
     return fail(MT_ERR_INVALID, "mt_free: %p was not allocated by mt_malloc (or freed twice)", p);
   Block& b = it->second;
+  if (b.foreign && g().ready && !P.capturing) {
+    Global& G = g();
+    if (b.foreign & 1) {
+      cudaEventRecord(G.ev_copy, G.copy_stream);
+      cudaStreamWaitEvent(G.stream, G.ev_copy, 0);
+    }
+    if (b.foreign & 2) {
+      cudaEventRecord(G.ev_comm, G.comm_stream);
+      cudaStreamWaitEvent(G.stream, G.ev_comm, 0);
+    }
+    b.foreign = 0;
+  }
   P.in_use -= b.size;
   if (b.graph == 0) {
     P.free_blocks.emplace(b.size, p);
@@ -218,6 +267,7 @@ MT_API int mt_init(int device) {
   MT_CUDA(cudaEventCreateWithFlags(&G.ev_copy_gate, cudaEventDisableTiming));
   MT_CUDA(cudaEventCreateWithFlags(&G.ev_compute, cudaEventDisableTiming));
   MT_CUDA(cudaEventCreateWithFlags(&G.ev_comm, cudaEventDisableTiming));
+  MT_CUDA(cudaEventCreateWithFlags(&G.ev_dw_ready, cudaEventDisableTiming));
   G.launches = 0;
   G.ready = true;
   return MT_OK;
@@ -232,6 +282,8 @@ MT_API int mt_shutdown(void) {
   G.l2_flush_buf = nullptr;
   cudaEventDestroy(G.ev_compute);
   cudaEventDestroy(G.ev_comm);
+  cudaEventDestroy(G.ev_dw_ready);
+  G.dw_ready_ptr = nullptr;
   cudaStreamDestroy(G.stream);
   cudaStreamDestroy(G.comm_stream);
   cudaStreamDestroy(G.copy_stream);
@@ -298,6 +350,35 @@ MT_API int mt_event_elapsed_ms(void* a, void* b, float* ms) {
 MT_API int mt_event_destroy(void* ev) {
   MT_REQUIRE_INIT();
   MT_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+  return MT_OK;
+}
+
+MT_API int mt_trace_enable(int on) {
+  MT_REQUIRE_INIT();
+  g().trace_on = on != 0;
+  if (on) trace_mark("trace_begin", g().stream, 0);
+  return MT_OK;
+}
+MT_API int mt_trace_reset(void) {
+  for (auto& r : g_trace) g_trace_pool.push_back(r.ev);
+  g_trace.clear();
+  return MT_OK;
+}
+MT_API int mt_trace_count(int* n) {
+  MT_CHECK_ARG(n, "mt_trace_count: null out pointer");
+  *n = (int)g_trace.size();
+  return MT_OK;
+}
+MT_API int mt_trace_get(int i, char* name, size_t cap, int* stream_id, float* ms_since_first) {
+  MT_REQUIRE_INIT();
+  MT_CHECK_ARG(i >= 0 && i < (int)g_trace.size(), "mt_trace_get: index %d out of range", i);
+  MT_CUDA(cudaEventSynchronize(g_trace[i].ev));
+  if (name && cap) {
+    strncpy(name, g_trace[i].name, cap - 1);
+    name[cap - 1] = 0;
+  }
+  if (stream_id) *stream_id = g_trace[i].stream_id;
+  if (ms_since_first) MT_CUDA(cudaEventElapsedTime(ms_since_first, g_trace[0].ev, g_trace[i].ev));
   return MT_OK;
 }
 
@@ -467,6 +548,7 @@ MT_API int mt_h2d_prefetch(void* dst, const void* pinned_src, size_t bytes) {
   MT_CUDA(cudaEventRecord(G.ev_copy_gate, G.stream));
   MT_CUDA(cudaStreamWaitEvent(G.copy_stream, G.ev_copy_gate, 0));
   MT_CUDA(cudaMemcpyAsync(dst, pinned_src, bytes, cudaMemcpyHostToDevice, G.copy_stream));
+  pool_mark_foreign(dst, 1);
   return MT_OK;
 }
 MT_API int mt_prefetch_wait(void) {
@@ -516,8 +598,9 @@ MT_API int mt_memset_multi(void* const* ptrs, const size_t* bytes, int count) {
     unsigned long long acc = 0;
     while (done < count && k < ZeroTable::CAP) {
       size_t b = bytes[done];
-      MT_CHECK_ARG((reinterpret_cast<uintptr_t>(ptrs[done]) & 15) == 0, "mt_memset_multi: pointer %d not 16 B aligned", done);
-      if (b % 16) {  // odd tail: plain memset for this one (rare: parameters are multiples of 4 floats)
+      if (b % 16 || (reinterpret_cast<uintptr_t>(ptrs[done]) & 15)) {
+        // odd tail or a mis-aligned view (an odd-offset slice): plain memset for this one (rare: parameters are
+        // pool blocks of whole float4s)
         MT_CUDA(cudaMemsetAsync(ptrs[done], 0, b, g().stream));
       } else if (b) {
         t.ptr[k] = (float*)ptrs[done];
@@ -539,7 +622,7 @@ MT_API int mt_memset_multi(void* const* ptrs, const size_t* bytes, int count) {
 
 __global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ out, size_t n, float v) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t n4 = n / 4;
+  const size_t n4 = (reinterpret_cast<uintptr_t>(out) & 15) ? 0 : n / 4;   // mis-aligned view: scalar stores only
   const float4 v4 = make_float4(v, v, v, v);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
     reinterpret_cast<float4*>(out)[i] = v4;

@@ -190,13 +190,33 @@ def clip(x, lo, hi):
 class linalg:                      # noqa: N801  (NumPy name)
     @staticmethod
     def norm(x, ord=2.0):          # noqa: A002
-        """Vector p-norm of all elements as a host float (the reference compares it on the host, tensor.py:308-309)."""
+        """np.linalg.norm(x, ord) as a host float (the reference compares it on the host, tensor.py:308-309), with
+        NumPy's meaning of `ord` per rank (Tensor.clip_grad_norm, reference src/tensor/tensor.py:297-310):
+          1-D  vector p-norm                                             - device reductions
+          2-D  ord=1 / inf: largest absolute column / row sum; 'fro'     - device reductions
+               ord=2: the SPECTRAL norm (largest singular value).  There is no SVD on the device: the gradient is
+               downloaded and NumPy's own SVD gives the value, so the scale factor is the reference's bit for bit.
+               Only this one scalar is computed on the host; the clipping multiply stays on the device.
+          other ranks raise like NumPy does when `ord` is given."""
         x = _as_device(x)
+        if x.ndim not in (1, 2):
+            raise ValueError("Improper number of dimensions to norm.")
         axes = tuple(range(x.ndim))
-        if ord == 2 or ord == 2.0:
+        if x.ndim == 2:
+            if ord == 2 or ord == -2:
+                return float(_np.linalg.norm(x.get(), ord))
+            if ord in (1, -1, _np.inf, -_np.inf):
+                sums = kernels.sum(kernels.unary(_capi.UN_ABS, x), axis=0 if ord in (1, -1) else 1)
+                return float(kernels.extreme(sums, None, False, ord in (1, _np.inf)).item())
+            if ord in ("fro", None):
+                return float(kernels.reduce_sum(x, axes, x).item()) ** 0.5
+            raise ValueError("Invalid norm order for matrices.")
+        if ord in (2, None):
             return float(kernels.reduce_sum(x, axes, x).item()) ** 0.5        # fused x*x reduction
-        if ord == 1 or ord == 1.0:
+        if ord == 1:
             return float(kernels.reduce_sum(kernels.unary(_capi.UN_ABS, x), axes).item())
+        if ord in (_np.inf, -_np.inf):
+            return float(kernels.extreme(kernels.unary(_capi.UN_ABS, x), None, False, ord == _np.inf).item())
         p = float(ord)
         powed = kernels.unary(_capi.UN_POW, kernels.unary(_capi.UN_ABS, x), p)
         return float(kernels.reduce_sum(powed, axes).item()) ** (1.0 / p)

@@ -165,7 +165,9 @@ class DeviceArray:
         return dense
 
     def _view(self, shape, strides, ptr=None) -> "DeviceArray":
-        return DeviceArray(self._block, self.ptr if ptr is None else ptr, shape, strides, self.dtype)
+        v = DeviceArray(self._block, self.ptr if ptr is None else ptr, shape, strides, self.dtype)
+        v._const = self._const          # a view of a shared read-only constant is read-only too
+        return v
 
     def dense(self) -> "DeviceArray":
         """self if already C-contiguous, else a materialised copy (one strided-gather kernel)."""

@@ -35,8 +35,12 @@ def binary(op: int, a, b, scalar: float = 0.0, out: Optional[DeviceArray] = None
     av, bv = a.broadcast_to(shape), b.broadcast_to(shape)
     if out is None:
         out = DeviceArray.empty(shape)
-    elif out.shape != shape or not out.is_dense:
-        raise ValueError("binary(out=): output must be a dense array of the broadcast shape")
+    else:
+        if out.shape != shape or not out.is_dense:
+            raise ValueError("binary(out=): output must be a dense array of the broadcast shape")
+        if out._const:
+            raise ValueError("binary(out=): the output is a shared read-only constant")
+        out._host_value = None
     if out.size:
         status = _lib().mt_ew_binary_f32(op, out.ptr, av.ptr, bv.ptr, len(shape), _capi.i64(shape), _capi.i64(av.strides),
                                          _capi.i64(bv.strides), float(scalar))

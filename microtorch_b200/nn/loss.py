@@ -55,9 +55,13 @@ class Loss(Module):
         value, dpred = backend.K.loss_forward_backward(self._kind, pred.data, target.data, count, pred.requires_grad)
         deps = []
         if pred.requires_grad:
+            from ..cuda.array import device_constant
+            seed = device_constant(1.0)         # what Tensor.backward() seeds a 0-d root with (read-only, shared)
+
             def to_pred(g):
-                # dpred already holds dL/dpred for an upstream gradient of 1 (the backward() seed)
-                if getattr(g, "_host_value", None) == 1.0:
+                # dpred already holds dL/dpred for an upstream gradient of 1 - recognised by IDENTITY with the shared
+                # constant, never by a host mirror of the value that a write through a view could leave stale
+                if g is seed:
                     return dpred
                 return backend.mul(dpred, g)
             deps.append(Leaf(value=pred, grad_fn=to_pred))

@@ -25,13 +25,16 @@ class SGD(Optimizer):
         super(SGD, self).__init__(parameters=parameters)
         self.lr = lr
 
-    def step(self) -> None:
+    def step(self, skip=None) -> None:
         """p <- p - lr * grad.  CUDA parameters are updated by ONE fused multi-tensor launch
         (reference: three kernels and two temporaries per parameter, optimizer.py:39 ->
         tensor.py:564-571).  A parameter whose gradient is still the unallocated zero - every
-        Linear bias, Q1 - is skipped: p - lr*0 == p."""
+        Linear bias, Q1 - is skipped: p - lr*0 == p.  `skip`: ids of parameters somebody already
+        updated in this step (the data-parallel trainer updates a weight right behind its all-reduce)."""
         dev_params, dev_grads = [], []
         for parameter in self.parameters():
+            if skip and id(parameter) in skip:
+                continue
             if parameter.device == Device.CUDA:
                 g = parameter._grad
                 if g is None or g is _LAZY:

@@ -587,9 +587,17 @@ class Tensor:
 # --------------------------------------------------------------------------- backward engine
 def _run_backward(root: Tensor, seed: Vector) -> None:
     """Reverse-topological sweep: every node receives the SUM of its incoming gradients once,
-    stores it, and pushes `grad_fn(sum)` to its sources.  Iterative (no recursion limit)."""
+    stores it, and pushes `grad_fn(sum)` to its sources.  Iterative (no recursion limit).
+
+    Interior nodes are visited in reversed depth-first post-order.  A node WITHOUT dependencies (a
+    Parameter, an input) is finalised the moment its last incoming edge has been processed rather than
+    at its place in that order - in the post-order every parameter sits behind ALL interior nodes, which
+    would delay the data-parallel trainer's gradient hooks (one all-reduce per weight, trainer.py) until
+    the whole backward pass had been queued.  The order in which a node's incoming gradients are summed is
+    the same either way."""
     order: List[Tensor] = []
     seen = set()
+    fan_in: Dict[int, int] = {}                     # tape edges pointing at each source tensor
     stack: List[Tuple[Tensor, int]] = [(root, 0)]
     while stack:                                    # post-order DFS without recursion
         node, i = stack.pop()
@@ -597,6 +605,9 @@ def _run_backward(root: Tensor, seed: Vector) -> None:
             if id(node) in seen:
                 continue
             seen.add(id(node))
+            for leaf in node._dependencies:
+                key = id(leaf.value)
+                fan_in[key] = fan_in.get(key, 0) + 1
         deps = node._dependencies
         if i < len(deps):
             stack.append((node, i + 1))
@@ -621,6 +632,12 @@ def _run_backward(root: Tensor, seed: Vector) -> None:
                 up = np.asarray(up)
             key = id(src)
             if key in pending:
-                pending[key] = backend.accumulate(pending[key], up)
+                up = backend.accumulate(pending[key], up)
+            left = fan_in[key] = fan_in[key] - 1
+            if left == 0 and not src._dependencies:
+                pending.pop(key, None)              # a dependency-free tensor is final now
+                src._receive(up)
+                if src._grad_hook is not None:
+                    src._grad_hook(src)
             else:
                 pending[key] = up

@@ -5,8 +5,11 @@ backward, SGD.  `DataParallelTrainer` is the new component BASELINE.json asks fo
 section 8e): one process per GPU, every rank holds a full replica and a contiguous row shard
 of the batch, weight gradients are summed with NCCL over NVLink.  Each weight's all-reduce
 is queued on the communication stream the moment that weight's gradient is final (a tape
-hook), so the exchange of layer L overlaps the backward GEMMs of the layers below it; the
-fused SGD launch waits for the communication stream.  The loss is scaled by the GLOBAL
+hook - the backward engine finalises a parameter as soon as its last incoming edge has been
+processed, and the exchange is gated on the dW GEMM alone, not on the dX GEMM queued behind
+it), and `W -= lr * dW_sum` follows on the same stream, so exchange AND update of layer L run
+under the backward GEMMs of the layers below it; only the first layer's are exposed.  The
+compute stream waits for the communication stream once, before the next reader of the weights.  The loss is scaled by the GLOBAL
 element count, so summed rank gradients equal the single-process gradients up to fp32
 summation order and no extra 1/world pass is needed.  Bias gradients are identically zero
 (Q1) and are never exchanged.
@@ -69,7 +72,11 @@ def _small_mlp_plan(model: Module, loss_fn: Loss, optimizer: SGD, x: Tensor, tar
         return None
     if any(a.out_features != b.in_features for a, b in zip(layers[:-1], layers[1:])):
         return None
-    if target.size != x.shape[0] * layers[-1].out_features:
+    # the per-step path and the reference assert pred.shape == target.shape ("Input and target must have the same
+    # shape", loss.py:29): the single-launch loop must not train on a transposed / differently shaped target.
+    # fit() accepts (B,) as well when it squeezes a width-1 prediction.
+    out = layers[-1].out_features
+    if tuple(target.shape) != (x.shape[0], out) and not (out == 1 and tuple(target.shape) == (x.shape[0],)):
         return None
     return layers, acts
 
@@ -86,9 +93,12 @@ def fit(model: Module, loss_fn: Loss, optimizer: SGD, x: Tensor, target: Tensor,
     `fused=False` forces the per-step path.  Afterwards parameters hold the trained weights and `.grad` the last
     step's gradients, exactly as after the loop."""
     plan = None if fused is False else _small_mlp_plan(model, loss_fn, optimizer, x, target)
-    if squeeze_dim is not None and plan is not None:
-        ok = x.shape[0] * plan[0][-1].out_features == target.size and plan[0][-1].out_features == 1
-        plan = plan if ok else None
+    if plan is not None:
+        # pred is (B, out), or (B,) after squeeze(1) of a width-1 prediction; anything else is the per-step path's
+        # business (it raises the reference's AssertionError)
+        want = (x.shape[0],) if squeeze_dim is not None else (x.shape[0], plan[0][-1].out_features)
+        if tuple(target.shape) != want or (squeeze_dim is not None and plan[0][-1].out_features != 1):
+            plan = None
     if plan is None:
         if fused:
             raise ValueError("fit(fused=True): the model / loss / batch do not qualify for the single-launch trainer")
@@ -189,6 +199,11 @@ class Communicator:
         """In-place sum over ranks, asynchronous on the communication stream."""
         _capi.check(self.lib.mt_allreduce_sum_f32(arr.ptr, arr.size), "mt_allreduce_sum_f32")
 
+    def allreduce_sgd_(self, param, grad, lr: float) -> None:
+        """grad <- sum over ranks; param -= lr * grad - both on the communication stream (mt_allreduce_sgd_f32)."""
+        _capi.check(self.lib.mt_allreduce_sgd_f32(param.ptr, grad.ptr, grad.size, float(lr)), "mt_allreduce_sgd_f32")
+        param._host_value = None
+
     def wait(self) -> None:
         _capi.check(self.lib.mt_comm_wait(), "mt_comm_wait")
 
@@ -219,8 +234,14 @@ class GlooCommunicator:
 
 class DataParallelTrainer:
     def __init__(self, model: Module, loss_fn: Loss, lr: float, comm: Optional[Communicator] = None,
-                 pred_map: Optional[Tuple[float, float]] = None, squeeze_dim: Optional[int] = None) -> None:
+                 pred_map: Optional[Tuple[float, float]] = None, squeeze_dim: Optional[int] = None,
+                 overlap: bool = True) -> None:
+        """`overlap=False` is the measurement baseline (tools/dp_timeline.py): every gradient is exchanged only after
+        the whole backward pass has been queued and all parameters are updated by the one fused SGD launch - what
+        round 1 effectively did (its hooks fired after the last backward GEMM)."""
         self.model, self.loss_fn = model, loss_fn
+        self.overlap = overlap
+        self._deferred = []
         self.comm = comm
         self.world = comm.world if comm is not None else 1
         self.loss_fn.world = self.world            # mean over the GLOBAL batch
@@ -228,6 +249,8 @@ class DataParallelTrainer:
         self.pred_map, self.squeeze_dim = pred_map, squeeze_dim
         self.exchanged_bytes = 0
         self.steps = 0
+        self.hook_order = []          # id(param) in the order the gradients became final (last step)
+        self._updated = set()         # parameters already updated behind their all-reduce in this step
 
     def _on_grad_final(self, param: Tensor) -> None:
         g = param._grad
@@ -238,7 +261,17 @@ class DataParallelTrainer:
         if isinstance(g, np.ndarray) and not g.flags.c_contiguous:
             g = np.ascontiguousarray(g)
             param._grad = g
-        self.comm.allreduce_(g)
+        self.hook_order.append(id(param))
+        if not self.overlap:
+            self._deferred.append(g)
+            self.exchanged_bytes += g.nbytes
+            return
+        fused_update = getattr(self.comm, "allreduce_sgd_", None)
+        if fused_update is not None and param.device == Device.CUDA and param.data.is_dense and g.size == param.data.size:
+            fused_update(param.data, g, self.optimizer.lr)
+            self._updated.add(id(param))
+        else:
+            self.comm.allreduce_(g)
         self.exchanged_bytes += g.nbytes
 
     def step(self, x: Tensor, target: Tensor) -> Tensor:
@@ -256,10 +289,15 @@ class DataParallelTrainer:
             # Parameter objects are replaced on the first forward (Q6): hook the current ones
             for p in model.parameters():
                 p._grad_hook = self._on_grad_final
+            self.hook_order = []
+            self._updated = set()
         loss.backward()
         if self.comm is not None and self.world > 1:
+            for g in self._deferred:
+                self.comm.allreduce_(g)
+            self._deferred = []
             self.comm.wait()
-        self.optimizer.step()
+        self.optimizer.step(skip=self._updated)
         self.steps += 1
         return loss
 

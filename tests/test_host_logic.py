@@ -198,3 +198,76 @@ def test_relu_sigmoid_activations_cpu():
     np.testing.assert_allclose(s.data, want, rtol=1e-6)
     s.sum().backward()
     np.testing.assert_allclose(x.grad, want * (1 - want), rtol=1e-5)
+
+
+def test_parameter_hooks_fire_as_soon_as_their_gradient_is_final():
+    """ADVICE r1 (tensor.py backward order): a Parameter is finalised the moment its last incoming edge has been
+    processed - the hook of layer L must fire BEFORE the grad_fn of layer L-1 runs, otherwise every gradient
+    all-reduce of the data-parallel trainer is queued behind the whole backward pass."""
+    from microtorch_b200.tensor import Tensor
+    from microtorch_b200.tensor.types import Leaf
+    rng = np.random.default_rng(0)
+    events = []
+    x = Tensor(rng.standard_normal((4, 3)).astype(np.float32))
+    weights = [Tensor(rng.standard_normal((3, 3)).astype(np.float32), requires_grad=True) for _ in range(3)]
+    h = x
+    for li, w in enumerate(weights):
+        w._grad_hook = (lambda t, li=li: events.append(("hook", li)))
+        inp = h
+
+        def gw(g, li=li, inp=inp):
+            events.append(("grad_fn_w", li))
+            return inp.data.T @ g
+
+        def gx(g, li=li, w=w):
+            events.append(("grad_fn_x", li))
+            return g @ w.data.T
+        deps = [Leaf(value=w, grad_fn=gw)]
+        if inp.requires_grad:
+            deps.append(Leaf(value=inp, grad_fn=gx))
+        h = Tensor(inp.data @ w.data, requires_grad=True, dependencies=deps)
+    h.sum().backward()
+    for li in (2, 1):
+        assert events.index(("hook", li)) < events.index(("grad_fn_w", li - 1)), events
+    assert [e for e in events if e[0] == "hook"] == [("hook", 2), ("hook", 1), ("hook", 0)]
+    # and the values are what the plain sweep gives
+    ref_h = [x.data]
+    for w in weights:
+        ref_h.append(ref_h[-1] @ w.data)
+    g = np.ones_like(ref_h[-1])
+    for li in (2, 1, 0):
+        np.testing.assert_allclose(weights[li].grad, ref_h[li].T @ g, rtol=1e-6)
+        g = g @ weights[li].data.T
+
+
+def test_shared_parameter_is_finalised_after_its_last_use_only():
+    """A tensor used twice receives the SUM of both edges, once, and its hook fires once."""
+    from microtorch_b200.tensor import Tensor
+    w = Tensor(np.array([2.0, 3.0], dtype=np.float32), requires_grad=True)
+    fired = []
+    w._grad_hook = lambda t: fired.append(np.array(t.grad))
+    y = (w * w + w).sum()
+    y.backward()
+    assert len(fired) == 1
+    np.testing.assert_allclose(fired[0], 2 * w.data + 1)
+    np.testing.assert_allclose(w.grad, 2 * w.data + 1)
+
+
+def test_single_launch_plan_rejects_a_target_of_another_shape():
+    """fit() must not train on a target whose SHAPE differs from pred (same element count)."""
+    from microtorch_b200.trainer import _small_mlp_plan
+    import microtorch_b200.nn as nn
+    from microtorch_b200.nn.activation import Tanh
+    from microtorch_b200.nn.loss import MSELoss
+    from microtorch_b200.nn.optimizer import SGD
+    from microtorch_b200.tensor.device import Device
+
+    class Fake:                                  # stands in for a CUDA tensor: only shape / device / ndim are read
+        def __init__(self, shape):
+            self.shape, self.device, self.ndim = shape, Device.CUDA, len(shape)
+            self.size = int(np.prod(shape))
+    model = nn.Sequential(nn.Linear(4, 6), Tanh(), nn.Linear(6, 3), Tanh())
+    opt = SGD(model.parameters, lr=0.1)
+    assert _small_mlp_plan(model, MSELoss(), opt, Fake((8, 4)), Fake((8, 3))) is not None
+    assert _small_mlp_plan(model, MSELoss(), opt, Fake((8, 4)), Fake((3, 8))) is None      # transposed
+    assert _small_mlp_plan(model, MSELoss(), opt, Fake((8, 4)), Fake((24,))) is None       # flattened

@@ -479,8 +479,7 @@ def test_select_family_and_l1loss_on_cuda_match_cpu_path(mt):
         else:
             np.testing.assert_allclose(host(l.data), ref[0], rtol=1e-6)
             np.testing.assert_array_equal(host(p.grad), ref[1])
-    # clip_grad_norm on a 1-D gradient (for >= 2-D the reference's np.linalg.norm(g, 2) is the matrix SPECTRAL norm -
-    # an accident of the NumPy API; the device path uses the vector 2-norm of all elements, like torch's clip_grad_norm_)
+    # clip_grad_norm on a 1-D gradient (matrices: test_parity_large_gpu.py::test_clip_grad_norm_matches_numpy_for_matrices)
     for dev in ("cpu", "cuda"):
         t = mt.Tensor(xv.reshape(-1), requires_grad=True, device=dev)
         (t * 3.0).sum().backward()
@@ -808,6 +807,9 @@ def test_full_size_step_against_the_oracle(mt):
     import full_size_parity
     rec = full_size_parity.run()
     assert rec["pass"], rec
+    if rec["batch"] != 65536:
+        pytest.skip(f"host memory too small for the B=65536 oracle ({rec['host_mem_available_gib']} GiB available): "
+                    f"the step was checked at batch {rec['batch']} only, which is NOT the full-size claim")
 
 
 def test_user_level_notebook_flow_on_cuda(mt):

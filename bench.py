@@ -55,13 +55,13 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index, period_ms=200):
+        self.rows, self.proc, self.gpu, self.period_ms = [], None, gpu_index, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -75,8 +75,14 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
+        return self.window(t0, t1)
+
+    def window(self, t0, t1):
+        """Clocks / throttle reasons of the samples taken in [t0, t1] (the sampler keeps running)."""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, reasons = [], [], set()
-        for ts, line in self.rows:
+        for ts, line in list(self.rows):
             if ts < t0 or ts > t1 + 0.3:
                 continue
             f = [x.strip() for x in line.split(",")]

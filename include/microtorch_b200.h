@@ -214,6 +214,11 @@ int mt_linear_bwd_f32(float* dX_or_null, float* dW, const float* dY, const float
 int mt_matmul_f32(float* C, const float* A, const float* B, int64_t batch, int64_t M, int64_t N,
                   int64_t K, int64_t a_sb, int64_t a_sm, int64_t a_sk, int64_t b_sb, int64_t b_sk,
                   int64_t b_sn);
+/* fp32 emulation level of the tensor-core GEMMs (like torch.set_float32_matmul_precision): 0 "high" (default: TF32 +
+ * 2 BF16 corrections, 1.4e-6 rms per GEMM), 1 "higher" (forward GEMMs on the all-TF32 split, 9e-7; +10 % per step),
+ * 2 "highest" (all-TF32 split with short accumulation chunks everywhere, 4.8e-7 = SGEMM class; +40 %).  Every level
+ * is far inside the 1e-4 GEMM tolerance per product; deep high-gain stacks amplify forward rounding. */
+int mt_gemm_set_precision(int level);
 /* which GEMM engine the last mt_linear_ / mt_matmul_ call used: 1 = tcgen05, 0 = SIMT fp32 */
 int mt_gemm_last_engine(int* engine);
 /* force the engine: -1 auto (default), 0 SIMT only, 1 tcgen05 only (error if the shape

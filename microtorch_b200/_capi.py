@@ -87,6 +87,7 @@ PROTOTYPES = {
     "mt_linear_fwd_f32": [VP, VP, VP, VP, C.c_int64, C.c_int64, C.c_int64, C.c_int],
     "mt_linear_bwd_f32": [VP, VP, VP, VP, VP, VP, C.c_int64, C.c_int64, C.c_int64, C.c_int],
     "mt_matmul_f32": [VP, VP, VP] + [C.c_int64] * 10,
+    "mt_gemm_set_precision": [C.c_int],
     "mt_gemm_last_engine": [C.POINTER(C.c_int)],
     "mt_gemm_set_engine": [C.c_int],
     "mt_loss_fwd_bwd_f32": [C.c_int, VP, VP, VP, VP, C.c_size_t, C.c_float],
@@ -176,6 +177,20 @@ def require_device(device: Optional[int] = None) -> None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
     check(lib().mt_init(device), "mt_init")
     _DEVICE_READY = True
+    level = os.environ.get("MICROTORCH_B200_MATMUL_PRECISION")
+    if level:
+        set_float32_matmul_precision(level)
+
+
+MATMUL_PRECISIONS = {"high": 0, "higher": 1, "highest": 2}
+
+
+def set_float32_matmul_precision(level: str) -> None:
+    """fp32 emulation level of the tensor-core GEMMs: "high" (default, fastest), "higher" (precise forward GEMMs),
+    "highest" (SGEMM-class everywhere).  See mt_gemm_set_precision in the header for the measured errors and costs."""
+    if level not in MATMUL_PRECISIONS:
+        raise ValueError(f"matmul precision must be one of {sorted(MATMUL_PRECISIONS)}, got {level!r}")
+    check(lib().mt_gemm_set_precision(MATMUL_PRECISIONS[level]), "mt_gemm_set_precision")
 
 
 def device_ready() -> bool:

@@ -21,6 +21,7 @@ struct GemmArgs {
                           // gradient straight from the dX epilogue: tanh' fused into the PRODUCER instead of a prologue)
   int act;                // mt_act
   int accumulate;         // C += result
+  int forward;            // a Linear forward product (its precision can be set apart: mt_gemm_tc_set_fwd)
   // SIMT split-K bookkeeping (filled by gemm_simt)
   int splits;
   long long kchunk;

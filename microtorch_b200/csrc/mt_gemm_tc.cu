@@ -344,6 +344,19 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   lo.z = __uint_as_float((__float_as_uint(v.z - hi.z) + 0x1000u) & 0xFFFFE000u);
   lo.w = __uint_as_float((__float_as_uint(v.w - hi.w) + 0x1000u) & 0xFFFFE000u);
 }
+// all-TF32 split with the CENTRED remainder (see centered_lo below): lo = tf32_rn((x - h (1 + c)) / (1 + c)).
+// Here the other factor of a correction product is the TRUNCATED operand h = (x - l) / (1 + c), not x, so
+//     A.B = S A_h.B_h + (1 + c)(A_l.B_h + A_h.B_l) + A_l.B_l,   S = (1 + c)^2
+// and the remainders are pre-divided by (1 + c) (instead of S as in the mix mode) for the epilogue's single scale S.
+__device__ __forceinline__ float centered_lo_tf32(float x);
+__device__ __forceinline__ float4 split4_centered(const float4 v) {
+  float4 lo;
+  lo.x = __uint_as_float((__float_as_uint(centered_lo_tf32(v.x)) + 0x1000u) & 0xFFFFE000u);
+  lo.y = __uint_as_float((__float_as_uint(centered_lo_tf32(v.y)) + 0x1000u) & 0xFFFFE000u);
+  lo.z = __uint_as_float((__float_as_uint(centered_lo_tf32(v.z)) + 0x1000u) & 0xFFFFE000u);
+  lo.w = __uint_as_float((__float_as_uint(centered_lo_tf32(v.w)) + 0x1000u) & 0xFFFFE000u);
+  return lo;
+}
 
 // ---- converter bodies.  All loads of a batch are issued before any dependent math or store: written as a
 // plain loop the compiler keeps load -> math -> store order per vector (the stores may alias the next load), which
@@ -360,13 +373,35 @@ __device__ __forceinline__ void convert_tile(uint8_t* raw_b, uint8_t* lo_b, int 
 #pragma unroll
     for (int u = 0; u < U; ++u) v[u] = raw[ct + (b + u) * 128];
 #pragma unroll
-    for (int u = 0; u < U; ++u) split4<WRITE_HI>(v[u], h[u], l[u]);
+    for (int u = 0; u < U; ++u) {
+      if (WRITE_HI) split4<true>(v[u], h[u], l[u]);
+      else l[u] = split4_centered(v[u]);          // hi = the tensor core's own truncation of the raw tile
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (WRITE_HI) raw[ct + (b + u) * 128] = h[u];
       lo[ct + (b + u) * 128] = l[u];
     }
   }
+}
+// mix mode: CENTERED remainder.  The tensor core TRUNCATES an fp32 operand to TF32, so with h = trunc_tf32(x) the plain
+// remainder x - h lies in [0, 2^-10)|x| - one-sided, and the dropped lo.lo term has a non-zero mean (a systematic
+// -2^-22 bias).  Writing x = h (1 + c) + l with c = 2^-11 centres it, |l| <= 2^-11 |h|, and since (1 + c) h = x - l:
+//     A.B = (1 + c)^2 A_h.B_h  +  A_l.B  +  A.B_l  -  A_l.B_l                     (exact)
+// The kernel accumulates  T = A_h.B_h + bf16(A_l / S).bf16(B) + bf16(A).bf16(B_l / S)  with S = (1 + c)^2 and the
+// epilogue multiplies by S (one fp32 multiply per output): same three products, same operands, but the remainders that
+// get rounded to BF16 are half as large - the rounding error of the two correction products, the error floor of the
+// mix mode, halves - and the dropped A_l.B_l (2^-24 / 3) is unbiased.  h (1 + c) needs 22 bits and x - h (1 + c) 12:
+// both exact in fp32 (measured before / after: tests/gemm_accuracy.py, profiles/r02_gemm_accuracy.jsonl).
+constexpr float kMixCenter = 1.00048828125f;          // 1 + 2^-11
+constexpr float kMixScale = 1.00097680091857910156f;  // S = (1 + 2^-11)^2 = 1 + 2^-10 + 2^-22, exact in fp32
+constexpr float kMixInvScale = 0.99902415275573730469f;   // 1 / S to fp32
+constexpr float kMixInvCenter = 0.99951195716857910156f;  // 1 / (1 + 2^-11) to fp32
+__device__ __forceinline__ float centered_lo(float x) {
+  return fmaf(-__uint_as_float(__float_as_uint(x) & 0xFFFFE000u), kMixCenter, x) * kMixInvScale;
+}
+__device__ __forceinline__ float centered_lo_tf32(float x) {
+  return fmaf(-__uint_as_float(__float_as_uint(x) & 0xFFFFE000u), kMixCenter, x) * kMixInvCenter;
 }
 // mix mode, K-major source: the fp32 tile (SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7)) is split
 // into bf16(x) and bf16(x - trunc_tf32(x)) and written as two SWIZZLE_64B tiles (64-byte rows; 16-byte chunk q of row r
@@ -391,10 +426,10 @@ __device__ __forceinline__ void convert_tile_mix_k(const uint8_t* raw_b, uint8_t
       if (b + u < PER && ct + (b + u) * NTHR < VECS) {
         const float4 x = v[u];
         float4 lo;
-        lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-        lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-        lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-        lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        lo.x = centered_lo(x.x);
+        lo.y = centered_lo(x.y);
+        lo.z = centered_lo(x.z);
+        lo.w = centered_lo(x.w);
         __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
         __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
         const int off = dst0 + (b + u) * (NTHR / 8) * 64;
@@ -431,10 +466,10 @@ __device__ __forceinline__ void convert_tile_mix_mn(const uint8_t* raw_b, uint8_
         const int off = box * 2048 + k * 64 + ((c32 ^ ((k >> 1) & 3)) << 4) + ((p16 & 1) << 3);
         const float4 x = v[u];
         float4 lo;
-        lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-        lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-        lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-        lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+        lo.x = centered_lo(x.x);
+        lo.y = centered_lo(x.y);
+        lo.z = centered_lo(x.z);
+        lo.w = centered_lo(x.w);
         __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
         __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
         *reinterpret_cast<uint2*>(hi16_b + off) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
@@ -763,7 +798,8 @@ gemm_splitfp32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           else mbar_arrive(tempty_bar(acc));
         }
       }
-      // ---- tile epilogue: bias, tanh, (accumulate), store.  One row per thread, 128 B per 32 columns.
+      // ---- tile epilogue: (mix-mode scale), bias, tanh, (accumulate), store.  One row per thread, 128 B per 32 columns.
+      const bool mix_scale = !PRO && (p.mix || !p.write_hi);   // centred split: accumulator scaled by S
       const long long row = m0 + quad * 32 + lane;
       if (row < p.M) {
         float* crow = p.C + (long long)work_split(w) * p.M * p.N + row * p.N;   // split partials are stacked
@@ -773,6 +809,7 @@ gemm_splitfp32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const long long n = nb0 + j;
           if (n < p.N) {                       // N % 4 == 0 (checked on the host)
             float4 v = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
+            if (mix_scale) { v.x *= kMixScale; v.y *= kMixScale; v.z *= kMixScale; v.w *= kMixScale; }
             if (p.bias) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
               v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -871,10 +908,11 @@ static int g_dbg_flags = 0;   // Params::dbg
 static int g_splitk = 1;      // allow split-K for badly quantised tile counts
 static int g_lo_stages = 3;   // lo ring depth; the raw ring gets whatever else fits (or g_raw_stages if > 0)
 static int g_raw_stages = 0;
+static int g_fwd_mix = -1, g_fwd_chunk_kb = -1;   // >= 0: override mix / chunk_kb for GEMMs flagged `forward`
 static int g_mix = 1;         // 1 (default): hi.hi on TF32, the two first-order corrections as BF16 products; 0: 3xTF32
 static int g_group_n = 0;     // tile order: 0 = choose per problem (see launch), > 0 = that many n-blocks per column group,
                               // < 0 = plain row-major order (all n-blocks in one group)
-static int g_hints = 3;       // bit 0: L2 eviction-priority hints on the operand loads, bit 1: streaming C stores
+static int g_hints = 6;       // bit 0: A loads evict_first, bit 1: streaming C stores, bit 2: B loads evict_last (see launch)
 static int g_pair = 1;        // 1: CTA pairs (cta_group::2) for N > 128 when the shape allows; 0: single CTAs only
 
 template <int BN, bool A_MN, bool B_MN, int NCTA, bool PRO>
@@ -905,9 +943,11 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   p.m_blocks = (int)ceil_div(a.M, BM * NCTA);
   p.n_blocks = (int)ceil_div(a.N, BN);
   p.k_blocks = (int)ceil_div(a.K, BK);
-  p.chunk_kb = g_chunk_kb > 0 ? g_chunk_kb : p.k_blocks;
+  const int want_mix = (a.forward && g_fwd_mix >= 0) ? g_fwd_mix : g_mix;
+  const int want_chunk = (a.forward && g_fwd_chunk_kb >= 0) ? g_fwd_chunk_kb : g_chunk_kb;
+  p.chunk_kb = want_chunk > 0 ? want_chunk : p.k_blocks;
   p.write_hi = g_write_hi;
-  p.mix = (g_mix && !PRO && !g_write_hi) ? 1 : 0;
+  p.mix = (want_mix && !PRO && !g_write_hi) ? 1 : 0;
   p.dbg = g_dbg_flags;
   {  // ring depths: lo ring g_lo_stages deep (default 3), raw ring takes the rest of the 227 KB
     int l = g_lo_stages, r = g_raw_stages;
@@ -964,7 +1004,7 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
     // so long that not even one group of B panels fits (dW: K = batch rows), nothing is reused across waves: no hints.
     const bool b_reused = p.group_n * b_panel <= (double)g().l2_bytes / 2.0 && p.m_blocks * p.group_n > unit_count;
     p.hint_a = ((g_hints & 1) && b_reused) ? 0x12F0000000000000ull : 0ull;
-    p.hint_b = ((g_hints & 1) && b_reused) ? 0x14F0000000000000ull : 0ull;
+    p.hint_b = ((g_hints & 4) && b_reused) ? 0x14F0000000000000ull : 0ull;
     // C streams out (evict-first) when it is far larger than L2 and nobody re-reads it soon (split-K partials are folded
     // right away: they keep the default policy)
     p.store_cs = ((g_hints & 2) && p.splits == 1 && (double)a.M * a.N * 4.0 > (double)g().l2_bytes / 2.0) ? 1 : 0;
@@ -1109,6 +1149,23 @@ MT_API int mt_prof_gemm(uint64_t* launches, double* ms_total, double* flops_tota
   return MT_OK;
 }
 
+// Precision policy of the tensor-core GEMMs (public: mt_gemm_set_precision in the header).  Per-GEMM error against
+// float64 (4096^3, rms relative; tests/gemm_accuracy.py, profiles/r02_gemm_accuracy.jsonl) and what it costs:
+//   0 "high"    (default) TF32 hi.hi + two BF16 corrections, centred remainders, TMEM chunks of K = 256:  1.4e-6
+//   1 "higher"  forward GEMMs with all three products on TF32 and chunks of K = 128, backward as "high":  9.0e-7 fwd
+//               (a deep, high-gain net amplifies FORWARD rounding ~100x into its gradients; backward hardly matters:
+//               config #5 at full width sits 1.3e-4 / 7.5e-5 / 5.3e-5 from the NumPy oracle at levels 0 / 1 / 2 - the
+//               oracle itself is 4e-5 from float64 there);                                  config #2 step +10 %
+//   2 "highest" all-TF32 split, chunks of K = 64, everywhere:  4.8e-7 (NumPy / OpenBLAS SGEMM: 3.7e-7)    step +40 %
+MT_API int mt_gemm_set_precision(int level) {
+  MT_CHECK_ARG(level >= 0 && level <= 2, "mt_gemm_set_precision: level must be 0 (high), 1 (higher) or 2 (highest)");
+  tc::g_mix = level == 2 ? 0 : 1;
+  tc::g_chunk_kb = level == 2 ? 2 : 8;
+  tc::g_fwd_mix = level == 1 ? 0 : -1;
+  tc::g_fwd_chunk_kb = level == 1 ? 4 : -1;
+  return MT_OK;
+}
+
 // diagnostic knobs (tests / hardware bring-up).
 //   write_hi : 1 = converters store a round-to-nearest hi explicitly, 0 (default) = the tensor core's own
 //              truncation of the raw fp32 operand is hi.
@@ -1135,7 +1192,7 @@ extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_dbg(int v) 
   return MT_OK;
 }
 //   group_n  : tile order - 0 (default) chosen per problem, n > 0 that many n-blocks per column group, < 0 row-major.
-//   hints    : bit 0 = L2 eviction-priority hints on operand loads, bit 1 = streaming stores of C (default 3).
+//   hints    : bit 0 = A loads evict_first, bit 1 = streaming stores of C, bit 2 = B loads evict_last.
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_group_n(int v) {
   tc::g_group_n = v;
   return MT_OK;
@@ -1150,6 +1207,12 @@ extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_pair(int v)
 }
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_chunk_kb(int v) {
   tc::g_chunk_kb = v < 0 ? 0 : v;
+  return MT_OK;
+}
+//   fwd      : precision of the FORWARD GEMMs only (mt_linear_fwd_f32): mix / chunk_kb as above, -1 = same as the rest.
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_fwd(int mix, int chunk_kb) {
+  tc::g_fwd_mix = mix;
+  tc::g_fwd_chunk_kb = chunk_kb;
   return MT_OK;
 }
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_mix(int v) {

@@ -44,6 +44,7 @@ MT_API int mt_linear_fwd_f32(float* Y, const float* X, const float* W, const flo
   a.a_sm = K; a.a_sk = 1;     // X row-major [M,K]
   a.b_sk = 1; a.b_sn = K;     // B(k,n) = W[n,k]
   a.bias = bias; a.act = act;
+  a.forward = 1;
   int engine = 1;
   int rc = run(a, &engine);
   g().gemm_last_engine = engine;

@@ -93,18 +93,23 @@ __global__ void __launch_bounds__(THREADS) reduce_rows_warp_kernel(float* __rest
 }
 
 // ------------------------------------------------------------ inner > 1: columns
-// block = TX column-vectors x TY row lanes; grid = (column tiles, splits, outer tiles)
-constexpr int TX = 64, TY = 4;
+// block = 256 threads = TX column-vectors x TY row lanes, TX = 2^tx_bits chosen on the host from `inner` (a (2^22, 8)
+// gradient folded onto a (1, 8) operand has 2 column-vectors: TX = 2, TY = 128 - with the fixed 64 x 4 shape of round 1
+// only 8 of 256 threads had work and the kernel ran at 17 % of HBM); grid = (column tiles, splits, outer tiles).
+// The row lanes are folded through shared memory in a fixed binary tree; each thread stores its V sums as ONE vector,
+// so the stores are conflict-free (the old [TY][TX*V+1] float layout was 4-way conflicted: 7.9 M conflicts per launch).
+constexpr int CT = 256;
 
 template <bool HAS_W, int V>
-__global__ void __launch_bounds__(TX* TY) reduce_cols_kernel(float* __restrict__ out, const float* __restrict__ x,
-                                                             long long outer, long long red, long long inner,
-                                                             long long splits, long long chunk,
-                                                             const float* __restrict__ w, long long so, long long sr,
-                                                             long long si) {
-  __shared__ float smem[TY][TX * V + 1];
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const long long col = ((long long)blockIdx.x * TX + tx) * V;
+__global__ void __launch_bounds__(CT) reduce_cols_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                         long long outer, long long red, long long inner,
+                                                         long long splits, long long chunk,
+                                                         const float* __restrict__ w, long long so, long long sr,
+                                                         long long si, int tx_bits) {
+  __shared__ __align__(16) float smem[CT * V];
+  const int TXr = 1 << tx_bits, TYr = CT >> tx_bits;
+  const int tx = threadIdx.x & (TXr - 1), ty = threadIdx.x >> tx_bits;
+  const long long col = ((long long)blockIdx.x * TXr + tx) * V;
   const long long s = blockIdx.y;
   const long long r0 = s * chunk;
   long long r1 = r0 + chunk;
@@ -118,12 +123,12 @@ __global__ void __launch_bounds__(TX* TY) reduce_cols_kernel(float* __restrict__
       const float* pw = HAS_W ? w + o * so + col * si : nullptr;
       long long r = r0 + ty;
       if (V == 4) {
-        for (; r + 3 * TY < r1; r += 4 * TY) {
+        for (; r + 3 * TYr < r1; r += 4 * TYr) {
           float4 a[4], b[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            a[u] = mtd::ld_stream4(px + (r + u * TY) * inner);
-            if (HAS_W) b[u] = mtd::ld_stream4(pw + (r + u * TY) * sr);
+            a[u] = mtd::ld_stream4(px + (r + u * TYr) * inner);
+            if (HAS_W) b[u] = mtd::ld_stream4(pw + (r + u * TYr) * sr);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(TX* TY) reduce_cols_kernel(float* __restrict__
             }
           }
         }
-        for (; r < r1; r += TY) {
+        for (; r < r1; r += TYr) {
           float4 a = mtd::ld_stream4(px + r * inner);
           if (HAS_W) {
             float4 b = mtd::ld_stream4(pw + r * sr);
@@ -144,20 +149,92 @@ __global__ void __launch_bounds__(TX* TY) reduce_cols_kernel(float* __restrict__
           }
         }
       } else {
-        for (; r < r1; r += TY) acc[0] += HAS_W ? px[r * inner] * pw[r * sr] : px[r * inner];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent loads in flight
+        for (; r + 3 * TYr < r1; r += 4 * TYr) {
+          if (HAS_W) {
+            a0 += px[r * inner] * pw[r * sr];
+            a1 += px[(r + TYr) * inner] * pw[(r + TYr) * sr];
+            a2 += px[(r + 2 * TYr) * inner] * pw[(r + 2 * TYr) * sr];
+            a3 += px[(r + 3 * TYr) * inner] * pw[(r + 3 * TYr) * sr];
+          } else {
+            a0 += px[r * inner];
+            a1 += px[(r + TYr) * inner];
+            a2 += px[(r + 2 * TYr) * inner];
+            a3 += px[(r + 3 * TYr) * inner];
+          }
+        }
+        for (; r < r1; r += TYr) a0 += HAS_W ? px[r * inner] * pw[r * sr] : px[r * inner];
+        acc[0] = (a0 + a1) + (a2 + a3);
       }
     }
-#pragma unroll
-    for (int v = 0; v < V; ++v) smem[ty][tx * V + v] = acc[v];
+    if (V == 4) reinterpret_cast<float4*>(smem)[threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else smem[threadIdx.x] = acc[0];
     __syncthreads();
+    for (int half = TYr >> 1; half > 0; half >>= 1) {      // fixed tree over the row lanes: deterministic
+      if (ty < half) {
+        if (V == 4) {
+          float4 a = reinterpret_cast<float4*>(smem)[threadIdx.x];
+          const float4 b = reinterpret_cast<float4*>(smem)[threadIdx.x + (half << tx_bits)];
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          reinterpret_cast<float4*>(smem)[threadIdx.x] = a;
+        } else {
+          smem[threadIdx.x] += smem[threadIdx.x + (half << tx_bits)];
+        }
+      }
+      __syncthreads();
+    }
     if (ty == 0 && col < inner) {
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        float t = (smem[0][tx * V + v] + smem[1][tx * V + v]) + (smem[2][tx * V + v] + smem[3][tx * V + v]);
-        out[(o * splits + s) * inner + col + v] = t;
-      }
+      float* po = out + (o * splits + s) * inner + col;
+      if (V == 4) *reinterpret_cast<float4*>(po) = reinterpret_cast<float4*>(smem)[threadIdx.x];
+      else po[0] = smem[threadIdx.x];
     }
     __syncthreads();
+  }
+}
+
+// few rows, many columns (the fold of stacked split-K partials, x.sum(axis=0) of a short-fat array): one thread per
+// column-vector walks all `red` rows itself - fully coalesced, no shared memory, no idle row lanes.
+template <bool HAS_W, int V>
+__global__ void __launch_bounds__(CT) reduce_cols_flat_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                              long long outer, long long red, long long inner,
+                                                              const float* __restrict__ w, long long so, long long sr,
+                                                              long long si) {
+  const long long vcols = inner / V;                      // V == 4: inner % 4 == 0 (checked on the host)
+  const long long total = outer * vcols;
+  const long long stride = (long long)gridDim.x * CT;
+  for (long long t = (long long)blockIdx.x * CT + threadIdx.x; t < total; t += stride) {
+    const long long o = t / vcols, col = (t - o * vcols) * V;
+    const float* px = x + (o * red) * inner + col;
+    const float* pw = HAS_W ? w + o * so + col * si : nullptr;
+    if (V == 4) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      long long r = 0;
+      for (; r + 3 < red; r += 4) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a[u] = mtd::ld_stream4(px + (r + u) * inner);
+          if (HAS_W) b[u] = mtd::ld_stream4(pw + (r + u) * sr);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (HAS_W) { acc.x += a[u].x * b[u].x; acc.y += a[u].y * b[u].y; acc.z += a[u].z * b[u].z; acc.w += a[u].w * b[u].w; }
+          else { acc.x += a[u].x; acc.y += a[u].y; acc.z += a[u].z; acc.w += a[u].w; }
+        }
+      }
+      for (; r < red; ++r) {
+        const float4 a = mtd::ld_stream4(px + r * inner);
+        if (HAS_W) {
+          const float4 b = mtd::ld_stream4(pw + r * sr);
+          acc.x += a.x * b.x; acc.y += a.y * b.y; acc.z += a.z * b.z; acc.w += a.w * b.w;
+        } else { acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w; }
+      }
+      *reinterpret_cast<float4*>(out + o * inner + col) = acc;
+    } else {
+      float acc = 0.f;
+      for (long long r = 0; r < red; ++r) acc += HAS_W ? px[r * inner] * pw[r * sr] : px[r * inner];
+      out[o * inner + col] = acc;
+    }
   }
 }
 
@@ -208,13 +285,28 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
                 long long so, long long sr, long long si) {
   cudaStream_t st = g().stream;
   const int sms = g().sm_count;
-  const bool vec = inner % 4 == 0 && aligned16(x) && (!w || (aligned16(w) && si == 1 && sr % 4 == 0 && so % 4 == 0));
+  const bool vec = inner % 4 == 0 && aligned16(x) && aligned16(out) &&
+                   (!w || (aligned16(w) && si == 1 && sr % 4 == 0 && so % 4 == 0));
   const int V = vec ? 4 : 1;
-  const long long tiles = ceil_div(inner, (long long)TX * V);
+  const long long vcols = ceil_div(inner, (long long)V);
+  if (red <= 16 && outer * vcols >= (long long)sms * CT) {      // short-fat: one thread per column-vector
+    const int grid = ew_grid(outer * vcols, CT);
+#define MT_FLAT(HW, VV) reduce_cols_flat_kernel<HW, VV><<<grid, CT, 0, st>>>(out, x, outer, red, inner, w, so, sr, si)
+    if (w) { if (vec) MT_FLAT(true, 4); else MT_FLAT(true, 1); }
+    else { if (vec) MT_FLAT(false, 4); else MT_FLAT(false, 1); }
+#undef MT_FLAT
+    MT_LAUNCHED();
+    return MT_OK;
+  }
+  int tx_bits = 0;
+  while (tx_bits < 6 && (1LL << tx_bits) < vcols) ++tx_bits;    // TX = min(64, pow2 >= column-vectors)
+  const int TXr = 1 << tx_bits, TYr = CT >> tx_bits;
+  const long long tiles = ceil_div(vcols, (long long)TXr);
   const long long oz = std::min<long long>(outer, 65535);
   long long splits = 1;
   if (tiles * oz < 4LL * sms) {
-    splits = std::min<long long>(ceil_div(4LL * sms, tiles * oz), ceil_div(red, 64));
+    // fill the machine (4 CTAs per SM) but leave every row lane at least ~8 rows of work
+    splits = std::min<long long>(ceil_div(4LL * sms, tiles * oz), ceil_div(red, (long long)TYr * 8));
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
   }
@@ -230,7 +322,8 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
     dst = partial;
   }
   dim3 grid((unsigned)tiles, (unsigned)splits, (unsigned)oz);
-#define MT_COLS(HW, VV) reduce_cols_kernel<HW, VV><<<grid, TX * TY, 0, st>>>(dst, x, outer, red, inner, splits, chunk, w, so, sr, si)
+#define MT_COLS(HW, VV) \
+  reduce_cols_kernel<HW, VV><<<grid, CT, 0, st>>>(dst, x, outer, red, inner, splits, chunk, w, so, sr, si, tx_bits)
   if (w) { if (vec) MT_COLS(true, 4); else MT_COLS(true, 1); }
   else { if (vec) MT_COLS(false, 4); else MT_COLS(false, 1); }
 #undef MT_COLS

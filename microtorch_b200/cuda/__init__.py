@@ -24,6 +24,11 @@ int16 = _np.int16
 int8 = _np.int8
 
 
+def set_float32_matmul_precision(level: str) -> None:
+    """"high" (default) | "higher" | "highest": fp32 emulation level of the tensor-core GEMMs (see _capi)."""
+    _capi.set_float32_matmul_precision(level)
+
+
 def is_available() -> bool:
     """True when the shared library loads and at least one CUDA device is visible."""
     return _capi.device_count() > 0

@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--once", action="store_true")
     ap.add_argument("--iters", type=int, default=8)
-    ap.add_argument("--settings", default="-1:0,0:0,0:3,8:3,4:3,-1:3")
+    ap.add_argument("--settings", default="-1:0,8:0,8:2,8:4,8:6,6:2,4:0,4:2")
     ap.add_argument("--rows", type=int, default=65536)
     args = ap.parse_args()
     lib = _capi.lib()
@@ -69,28 +69,38 @@ def main():
         return lib.mt_matmul_f32(dX.ptr, dZ.ptr, W2.ptr, 1, B, 4096, 4096, 0, 4096, 1, 0, 4096, 1)
     ops["dX2_65536x4096x4096"] = (dx_only, 2.0 * B * 4096 * 4096, 4.0 * (2 * B * 4096 + 4096 * 4096))
 
-    for setting in args.settings.split(","):
-        gn, hints = (int(v) for v in setting.split(":"))
+    settings = [tuple(int(v) for v in st.split(":")) for st in args.settings.split(",")]
+
+    def apply(gn, hints):
         lib.mt_gemm_tc_set_group_n(gn)
         lib.mt_gemm_tc_set_hints(hints)
-        for name, (fn, flops, alg) in ops.items():
-            if args.once:
+
+    if args.once:
+        for gn, hints in settings:
+            apply(gn, hints)
+            for name, (fn, flops, alg) in ops.items():
                 _capi.check(fn(), name)
                 _capi.check(lib.mt_sync())
                 print(json.dumps({"op": name, "group_n": gn, "hints": hints, "alg_bytes": alg}), flush=True)
-                continue
-            for _ in range(2):
-                _capi.check(fn(), name)
-            ts = []
-            for _ in range(args.iters):
-                lib.mt_event_record(e0)
-                _capi.check(fn(), name)
-                lib.mt_event_record(e1)
-                lib.mt_event_sync(e1)
-                ms = C.c_float()
-                lib.mt_event_elapsed_ms(e0, e1, C.byref(ms))
-                ts.append(ms.value)
+    else:
+        # INTERLEAVED: under the power cap the clock sinks while the GPU warms up, so timing one setting after the other
+        # favours whichever comes first; every repetition visits every (setting, op) once instead
+        times = {}
+        for rep in range(args.iters + 2):
+            for gn, hints in settings:
+                apply(gn, hints)
+                for name, (fn, flops, alg) in ops.items():
+                    lib.mt_event_record(e0)
+                    _capi.check(fn(), name)
+                    lib.mt_event_record(e1)
+                    lib.mt_event_sync(e1)
+                    ms = C.c_float()
+                    lib.mt_event_elapsed_ms(e0, e1, C.byref(ms))
+                    if rep >= 2:
+                        times.setdefault((gn, hints, name), []).append(ms.value)
+        for (gn, hints, name), ts in times.items():
             ts.sort()
+            flops, alg = ops[name][1], ops[name][2]
             print(json.dumps({"op": name, "group_n": gn, "hints": hints, "ms_min": ts[0], "ms_med": ts[len(ts) // 2],
                               "tflops_at_med": flops / ts[len(ts) // 2] / 1e9, "alg_gb": alg / 1e9}), flush=True)
     lib.mt_gemm_tc_set_group_n(0)

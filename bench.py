@@ -251,6 +251,9 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="rows per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c5", action="store_true", help="skip the config #5 sub-object")
+    ap.add_argument("--precision", default="higher", choices=["high", "higher", "highest"],
+                    help="fp32 emulation level of the tensor-core GEMMs (library default: higher)")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the precision=high sub-object")
     args = ap.parse_args()
     # stdout carries exactly ONE line - the JSON result.  Libraries write banners to fd 1 (NCCL prints its version
     # there when NCCL_DEBUG asks for it), so everything else is sent to stderr for the duration of the run.
@@ -280,6 +283,7 @@ def main():
     from microtorch_b200 import _capi, workloads as W
     _capi.require_device(local_rank)
     lib = _capi.lib()
+    _capi.set_float32_matmul_precision(args.precision)
     import microtorch_b200.nn as nn
     from microtorch_b200.cuda import kernels as K
     from microtorch_b200.cuda.array import DeviceArray
@@ -364,10 +368,19 @@ def main():
     t_wall1 = time.time()
     launches = C.c_uint64()
     lib.mt_launch_count(C.byref(launches))
-    n_gemm, gemm_ms, gemm_flops = C.c_uint64(), C.c_double(), C.c_double()
-    lib.mt_prof_gemm(C.byref(n_gemm), C.byref(gemm_ms), C.byref(gemm_flops))
+    n_gemm, gemm_ms, gemm_flops, gemm_unit_flops = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
+    lib.mt_prof_gemm_units(C.byref(n_gemm), C.byref(gemm_ms), C.byref(gemm_flops), C.byref(gemm_unit_flops))
     lib.mt_prof_enable(0)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    per_rank = None
+    if dist is not None:
+        # every rank's own tcgen05 time per step: under the power cap the chips of one box do not run at the same
+        # clock, and the step of a data-parallel job is paced by the slowest one - that spread is not communication
+        import torch
+        mine = torch.tensor([gemm_ms.value / args.steps], dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"gemm_ms_per_step_by_rank": [round(float(a[0]), 3) for a in allr]}
     loss_value = trainer.global_loss(last["loss"])
     samples = args.batch * world * args.steps
     value = samples / (ms_total / 1e3)
@@ -394,6 +407,61 @@ def main():
     e2e_steps = args.steps          # the same number of steps as `value` (under the power cap 10 vs 20 steps differ)
     ms_e2e = timed(step_e2e, e2e_steps)
     e2e_value = args.batch * world * e2e_steps / (ms_e2e / 1e3)
+
+    # ------------------------------------------------------------- the opt-in fast mode, for information (N = 1)
+    fast = None
+    if world == 1 and args.precision != "high" and not args.no_fast_mode:
+        _capi.set_float32_matmul_precision("high")
+        for _ in range(2):
+            step_resident()
+        fsteps = max(3, args.steps // 2)
+        ms_fast = timed(step_resident, fsteps)
+        fast = {"matmul_precision": "high", "value": args.batch * fsteps / (ms_fast / 1e3), "unit": "samples/s",
+                "ms_per_step": ms_fast / fsteps, "steps": fsteps,
+                "note": "every GEMM as TF32 hi.hi + 2 BF16 corrections; config #5 at full width then sits 1.3e-4 from the "
+                        "oracle end to end (tests/test_parity_large_gpu.py), which is why it is not the default"}
+        _capi.set_float32_matmul_precision(args.precision)
+
+    # ------------------------------------------------------------- what data parallelism costs, same process (N > 1)
+    dp_overhead = None
+    if world > 1:
+        # the same step WITHOUT the communicator (independent replicas: every GPU at its own pace) against the
+        # data-parallel step, interleaved on the same GPUs: the ratio of the two max-over-ranks times is the cost of the
+        # exchange itself, free of the box-to-box and chip-to-chip clock spread that a comparison with a separate
+        # N = 1 run carries (tools/dp_ab.py is the long form of this measurement)
+        np.random.seed(wl.seed)
+        solo = DataParallelTrainer(W.build_model(wl, nn.Linear, Tanh, nn.Sequential),
+                                   CrossEntropyLoss() if wl.loss == "ce" else MSELoss(), wl.lr, None, wl.pred_map, wl.squeeze_dim)
+        for _ in range(3):
+            solo.step(X, T)
+        import torch
+        t_solo, t_dp, mine_solo = [], [], []
+        k = max(3, min(args.steps, 8))
+        for _ in range(3):
+            barrier()
+            lib.mt_event_record(ev0)
+            for _ in range(k):
+                solo.step(X, T)
+            lib.mt_event_record(ev1)
+            lib.mt_event_sync(ev1)
+            barrier()
+            ms = C.c_float()
+            lib.mt_event_elapsed_ms(ev0, ev1, C.byref(ms))
+            mine_solo.append(ms.value / k)
+            t_solo.append(max_over_ranks(ms.value) / k)
+            t_dp.append(timed(step_resident, k) / k)
+        mine = torch.tensor([statistics.median(mine_solo)], dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        solo_by_rank = [round(float(a[0]), 3) for a in allr]
+        dp_overhead = {"replicas_ms_per_step_max_over_ranks": statistics.median(t_solo),
+                       "data_parallel_ms_per_step_max_over_ranks": statistics.median(t_dp),
+                       "overhead": statistics.median(t_dp) / statistics.median(t_solo) - 1.0,
+                       "replicas_ms_per_step_by_rank": solo_by_rank,
+                       "chip_spread": max(solo_by_rank) / min(solo_by_rank) - 1.0,
+                       "rounds": 3, "steps_per_round": k,
+                       "how": "same process, same GPUs, interleaved: independent replicas (no communicator) vs the data-parallel step"}
+        solo = None
 
     # ------------------------------------------------------------- BASELINE config #5 (the named data-parallel config)
     c5 = None
@@ -431,9 +499,11 @@ def main():
         return
 
     peaks = load_peaks()
-    # fp32-emulated peak: one logical multiply-add costs one TF32 product (= 2 bf16-rate units) for hi.hi plus two BF16
-    # products for the first-order corrections = 4 units, so the logical peak is (bf16 dense peak) / 4
-    EMU = 4.0
+    # fp32-emulated peak: a logical multiply-add costs 4 bf16-rate units on the tensor pipe as TF32 hi.hi (2) + two BF16
+    # correction products (backward GEMMs, and every GEMM at precision "high"), 6 units as 3xTF32 (forward GEMMs at
+    # the default precision "higher").  EMU is the flop-weighted mean over the GEMM launches of the timed region (the
+    # library reports it per launch), so the logical peak is (bf16 dense peak) / EMU
+    EMU = gemm_unit_flops.value / gemm_flops.value if gemm_flops.value else 4.0
     peak_tf = peaks["bf16_sustained"] / EMU
     achieved_tf = (gemm_flops.value / n_gemm.value) / ((gemm_ms.value / n_gemm.value) * 1e-3) / 1e12 if n_gemm.value else 0.0
     out = {
@@ -443,7 +513,11 @@ def main():
         "config": {"workload": ("c2_mlp_1024_4096_4096_10_tanh_ce_sgd" if args.workload == "c2" else "c5_mlp_4096x8_tanh_mse_sgd"),
                    "per_gpu_batch": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (activations 1 GiB per layer); no flush needed",
-                   "gemm": "tcgen05 split-fp32 (TF32 hi.hi + 2 BF16 corrections per k-slice), chunked TMEM accumulation"},
+                   "matmul_precision": args.precision,
+                   "gemm": "tcgen05 split-fp32, chunked TMEM accumulation: " +
+                           {"high": "TF32 hi.hi + 2 BF16 corrections per k-slice in every GEMM",
+                            "higher": "forward GEMMs 3xTF32, backward GEMMs TF32 hi.hi + 2 BF16 corrections",
+                            "highest": "3xTF32 in every GEMM"}[args.precision]},
         "loss": loss_value,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(x_host.nbytes + t_host.nbytes) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
@@ -456,14 +530,22 @@ def main():
                      "traffic_unit": "bytes per launch (dram read+write, ncu --set full capture under profiles/)",
                      "launches": int(n_gemm.value), "kernel_ms_per_step": gemm_ms.value / args.steps,
                      "share_of_step": (gemm_ms.value / args.steps) / (ms_total / args.steps),
-                     "peak_source": f"{peaks['source']}: bf16 sustained {peaks['bf16_sustained']} TF/s / 4 (per logical multiply-add: one "
-                                    "TF32 product = 2 bf16-rate units, plus two BF16 correction products) - fp32-emulated peak; "
-                                    "burst would be %.1f" % (peaks["bf16"] / EMU)},
+                     "bf16_units_per_logical_mac": EMU,
+                     "peak_source": f"{peaks['source']}: bf16 sustained {peaks['bf16_sustained']} TF/s / {EMU:.3f} - the flop-weighted "
+                                    "bf16-rate units per logical multiply-add of this step's GEMMs (TF32 product = 2 units, BF16 "
+                                    "product = 1: 3xTF32 forward = 6, TF32 + 2 BF16 backward = 4) - fp32-emulated peak; burst "
+                                    "would be %.1f" % (peaks["bf16"] / EMU)},
     }
     if dp_parity is not None:
         out["dp_parity"] = dp_parity
+    if dp_overhead is not None:
+        out["dp_overhead"] = dp_overhead
+    if per_rank is not None:
+        out["ranks"] = per_rank
     if c5 is not None:
         out["c5"] = c5
+    if fast is not None:
+        out["fast_mode"] = fast
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     emit(out)

@@ -81,6 +81,10 @@ int mt_l2_flush(void);
 int mt_prof_enable(int on);
 int mt_prof_reset(void);
 int mt_prof_gemm(uint64_t* launches, double* ms_total, double* flops_total);
+/* same, plus the flops weighted by what each launch costs on the tensor pipe in bf16-rate units per logical
+ * multiply-add (TF32 product = 2, BF16 product = 1: 4 for the TF32 + 2xBF16 split, 6 for 3xTF32) - the numerator of
+ * the roofline fraction against the measured bf16 peak when launches of both kinds are mixed                   */
+int mt_prof_gemm_units(uint64_t* launches, double* ms_total, double* flops_total, double* unit_flops_total);
 
 /* ---------------------------------------------------------------- memory ---------- */
 /* replaces: CuPy's default MemoryPool behind every cp.array / zeros_like / operator
@@ -214,10 +218,14 @@ int mt_linear_bwd_f32(float* dX_or_null, float* dW, const float* dY, const float
 int mt_matmul_f32(float* C, const float* A, const float* B, int64_t batch, int64_t M, int64_t N,
                   int64_t K, int64_t a_sb, int64_t a_sm, int64_t a_sk, int64_t b_sb, int64_t b_sk,
                   int64_t b_sn);
-/* fp32 emulation level of the tensor-core GEMMs (like torch.set_float32_matmul_precision): 0 "high" (default: TF32 +
- * 2 BF16 corrections, 1.4e-6 rms per GEMM), 1 "higher" (forward GEMMs on the all-TF32 split, 9e-7; +10 % per step),
- * 2 "highest" (all-TF32 split with short accumulation chunks everywhere, 4.8e-7 = SGEMM class; +40 %).  Every level
- * is far inside the 1e-4 GEMM tolerance per product; deep high-gain stacks amplify forward rounding. */
+/* fp32 emulation level of the tensor-core GEMMs (like torch.set_float32_matmul_precision):
+ *   0 "high"    every GEMM as TF32 hi.hi + 2 BF16 correction products (1.4e-6 rms per GEMM): the fast, opt-in mode;
+ *   1 "higher"  DEFAULT - forward GEMMs as 3xTF32 (all three products on TF32, 9e-7), backward GEMMs as level 0;
+ *               +10-12 % per training step over level 0;
+ *   2 "highest" 3xTF32 with short accumulation chunks everywhere (4.8e-7 = SGEMM class); +40 %.
+ * Every level is far inside the 1e-4 GEMM tolerance per product.  Deep high-gain stacks amplify FORWARD rounding
+ * (BASELINE config #5 at full width: 1.3e-4 / 7.5e-5 / 5.3e-5 from the NumPy oracle end to end at levels 0 / 1 / 2),
+ * which is why level 1 is the default: the cheapest level that keeps every BASELINE config within 1e-4. */
 int mt_gemm_set_precision(int level);
 /* which GEMM engine the last mt_linear_ / mt_matmul_ call used: 1 = tcgen05, 0 = SIMT fp32 */
 int mt_gemm_last_engine(int* engine);

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "mt_prof_enable": [C.c_int],
     "mt_prof_reset": [],
     "mt_prof_gemm": [c_u64p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "mt_prof_gemm_units": [c_u64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)],
     "mt_malloc": [c_voidpp, C.c_size_t],
     "mt_free": [VP],
     "mt_pool_stats": [c_sizep, c_sizep, c_sizep, c_u64p, c_u64p],
@@ -186,8 +187,9 @@ MATMUL_PRECISIONS = {"high": 0, "higher": 1, "highest": 2}
 
 
 def set_float32_matmul_precision(level: str) -> None:
-    """fp32 emulation level of the tensor-core GEMMs: "high" (default, fastest), "higher" (precise forward GEMMs),
-    "highest" (SGEMM-class everywhere).  See mt_gemm_set_precision in the header for the measured errors and costs."""
+    """fp32 emulation level of the tensor-core GEMMs: "high" (fastest, opt-in), "higher" (default: 3xTF32 forward
+    GEMMs), "highest" (SGEMM-class everywhere).  See mt_gemm_set_precision in the header for the measured errors and
+    costs."""
     if level not in MATMUL_PRECISIONS:
         raise ValueError(f"matmul precision must be one of {sorted(MATMUL_PRECISIONS)}, got {level!r}")
     check(lib().mt_gemm_set_precision(MATMUL_PRECISIONS[level]), "mt_gemm_set_precision")

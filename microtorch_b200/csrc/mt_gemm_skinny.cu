@@ -22,7 +22,6 @@ namespace {
 
 constexpr int THREADS = 512;
 constexpr int RB = 4;                       // rows per warp iteration (register blocking over the smem-resident W)
-constexpr int SMEM_W_MAX = 200 * 1024;
 int g_skinny_ring = 1;                      // dW: 1 = cp.async ring, 0 = register double buffer (mt_gemm_set_skinny_ring)
 
 __device__ __forceinline__ float dot4_acc(const float4 a, const float4 b, float c) {
@@ -30,60 +29,85 @@ __device__ __forceinline__ float dot4_acc(const float4 a, const float4 b, float 
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int NP>
-__global__ void __launch_bounds__(THREADS) skinny_fwd_kernel(float* __restrict__ Y, const float* __restrict__ X,
-                                                             const float* __restrict__ W, const float* __restrict__ bias,
-                                                             long long M, int N, long long K, long long ldx, long long ldw,
-                                                             int act) {
-  extern __shared__ float4 Ws[];            // [N][K/4]
-  const int K4 = (int)(K >> 2);
+// W lives in shared memory CHUNK-major: the N rows' float4 of column-vector c sit together at Ws[c * NS + n] with an
+// ODD stride NS = N | 1, so (a) one address per chunk and N LDS.128 with immediate offsets instead of an index
+// computation per row, and (b) the 8 lanes of an LDS.128 phase hit 8 different 16-byte bank groups: conflict-free.
+// N is a template parameter (no predicate, no dead accumulators).  Round 1's kernel ([n][K4] layout, N padded to a
+// multiple of 4) issued 390 instructions per warp-chunk for 160 FMAs and was issue-bound at 63 % of HBM
+// (profiles/r02_hbm_kernels_ncu_raw.csv: 205 M warp instructions, issue slots 63 % busy at 25 % occupancy).
+template <int N>
+__device__ __forceinline__ void fill_w_chunk_major(float4* Ws, const float* __restrict__ W, int K4, long long ldw) {
+  constexpr int NS = N | 1;
   for (int i = threadIdx.x; i < N * K4; i += THREADS) {
     const int n = i / K4, c = i - n * K4;
-    Ws[i] = __ldg(reinterpret_cast<const float4*>(W + n * ldw) + c);
+    Ws[c * NS + n] = __ldg(reinterpret_cast<const float4*>(W + n * ldw) + c);
   }
+}
+
+template <int N>
+__global__ void __launch_bounds__(THREADS) skinny_fwd_kernel(float* __restrict__ Y, const float* __restrict__ X,
+                                                             const float* __restrict__ W, const float* __restrict__ bias,
+                                                             long long M, long long K, long long ldx, long long ldw,
+                                                             int act) {
+  constexpr int NS = N | 1;
+  extern __shared__ float4 Ws[];            // [K/4][NS]
+  const int K4 = (int)(K >> 2);
+  fill_w_chunk_major<N>(Ws, W, K4, ldw);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warps = (long long)gridDim.x * (THREADS / 32);
   for (long long r0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * RB; r0 < M; r0 += warps * RB) {
-    float acc[RB][NP];
+    float acc[RB][N];
+    const float4* xr[RB];                   // rows past the end re-read row M-1 (never stored): no per-row predicates
 #pragma unroll
-    for (int i = 0; i < RB; ++i)
+    for (int i = 0; i < RB; ++i) {
+      xr[i] = reinterpret_cast<const float4*>(X + (r0 + i < M ? r0 + i : M - 1) * ldx);
 #pragma unroll
-      for (int n = 0; n < NP; ++n) acc[i][n] = 0.f;
-    // software pipeline: the loads of chunk c+32 are issued before the FMAs of chunk c, so every warp keeps RB
-    // 128-bit loads in flight while it computes (the smem-resident W costs one LDS.128 per 4*RB FMAs)
-    float4 xc[RB];
+      for (int n = 0; n < N; ++n) acc[i][n] = 0.f;
+    }
+    // software pipeline, two chunks deep: 2 x RB 128-bit loads per lane (64 KB per SM) are in flight while chunk c is
+    // folded in (bandwidth x latency is ~44 KB per SM)
+    // (N > 10: the third buffer does not fit under the 128-register cap of a 512-thread CTA - one chunk ahead)
+    constexpr bool DEEP = N <= 10;
+    constexpr int AHEAD = DEEP ? 64 : 32;
+    float4 xa[RB], xb[RB];
 #pragma unroll
-    for (int i = 0; i < RB; ++i)
-      xc[i] = (r0 + i < M && lane < K4) ? mtd::ld_stream4(X + (r0 + i) * ldx + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < RB; ++i) {
+      xa[i] = lane < K4 ? mtd::ld_stream4(reinterpret_cast<const float*>(xr[i] + lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (DEEP)
+        xb[i] = lane + 32 < K4 ? mtd::ld_stream4(reinterpret_cast<const float*>(xr[i] + lane + 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll(DEEP ? 3 : 1)
     for (int c = lane; c < K4; c += 32) {
-      float4 xn[RB];
-      const bool more = (c + 32 < K4);
+      float4 xf[RB];
+      const bool more = c + AHEAD < K4;
 #pragma unroll
       for (int i = 0; i < RB; ++i)
-        xn[i] = (more && r0 + i < M) ? mtd::ld_stream4(X + (r0 + i) * ldx + 4 * (c + 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xf[i] = more ? mtd::ld_stream4(reinterpret_cast<const float*>(xr[i] + c + AHEAD)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* wp = Ws + c * NS;
 #pragma unroll
-      for (int n = 0; n < NP; ++n) {
-        if (n < N) {
-          const float4 w = Ws[n * K4 + c];
+      for (int n = 0; n < N; ++n) {
+        const float4 w = wp[n];
 #pragma unroll
-          for (int i = 0; i < RB; ++i) acc[i][n] = dot4_acc(xc[i], w, acc[i][n]);   // 4 FMAs, no separate add
-        }
+        for (int i = 0; i < RB; ++i) acc[i][n] = dot4_acc(xa[i], w, acc[i][n]);   // 4 FMAs, no separate add
       }
 #pragma unroll
-      for (int i = 0; i < RB; ++i) xc[i] = xn[i];
+      for (int i = 0; i < RB; ++i) {
+        if (DEEP) { xa[i] = xb[i]; xb[i] = xf[i]; }
+        else xa[i] = xf[i];
+      }
     }
 #pragma unroll
     for (int i = 0; i < RB; ++i)
 #pragma unroll
-      for (int n = 0; n < NP; ++n) acc[i][n] = mtd::warp_sum(acc[i][n]);
+      for (int n = 0; n < N; ++n) acc[i][n] = mtd::warp_sum(acc[i][n]);
     // lanes 0..N-1 each finish one output column of the RB rows
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
       if (r0 + i < M) {
         float v = 0.f;
 #pragma unroll
-        for (int n = 0; n < NP; ++n)
+        for (int n = 0; n < N; ++n)
           if (lane == n) v = acc[i][n];
         if (lane < N) {
           if (bias) v += __ldg(bias + lane);
@@ -108,58 +132,57 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 constexpr int DW_STAGES = 4;                // ring depth of skinny_dw_ring_kernel (one X row slice per stage)
 
 // ------------------------------------------------------------------------------------------------ dX
-template <int NP>
+// same shared-memory plan as the forward kernel (chunk-major W, odd stride, N a template parameter)
+template <int N>
 __global__ void __launch_bounds__(THREADS) skinny_dx_kernel(float* __restrict__ dX, const float* __restrict__ dZ,
                                                             const float* __restrict__ W, const float* __restrict__ epi_tanh,
-                                                            long long M, int N, long long K, long long ldz, long long ldw) {
-  extern __shared__ float4 Ws[];            // [N][K/4]
+                                                            long long M, long long K, long long ldz, long long ldw) {
+  constexpr int NS = N | 1;
+  extern __shared__ float4 Ws[];            // [K/4][NS]
   const int K4 = (int)(K >> 2);
-  for (int i = threadIdx.x; i < N * K4; i += THREADS) {
-    const int n = i / K4, c = i - n * K4;
-    Ws[i] = __ldg(reinterpret_cast<const float4*>(W + n * ldw) + c);
-  }
+  fill_w_chunk_major<N>(Ws, W, K4, ldw);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warps = (long long)gridDim.x * (THREADS / 32);
   for (long long r0 = ((long long)blockIdx.x * (THREADS / 32) + warp) * RB; r0 < M; r0 += warps * RB) {
-    float dz[RB][NP];
+    float dz[RB][N];
+    long long roff[RB];                    // row offset into dX and (same shape) the saved activations
 #pragma unroll
     for (int i = 0; i < RB; ++i) {
-      const float mine = (lane < N && r0 + i < M) ? __ldg(dZ + (r0 + i) * ldz + lane) : 0.f;
+      const long long r = r0 + i < M ? r0 + i : M - 1;
+      const float mine = lane < N ? __ldg(dZ + r * ldz + lane) : 0.f;
 #pragma unroll
-      for (int n = 0; n < NP; ++n) dz[i][n] = __shfl_sync(0xffffffffu, mine, n);
+      for (int n = 0; n < N; ++n) dz[i][n] = __shfl_sync(0xffffffffu, mine, n);
+      roff[i] = r * K;
     }
     float4 tc[RB];                         // saved activations of chunk c (tanh' epilogue), loaded one chunk ahead
 #pragma unroll
     for (int i = 0; i < RB; ++i)
-      tc[i] = (epi_tanh && r0 + i < M && lane < K4) ? mtd::ld_stream4(epi_tanh + (r0 + i) * K + 4 * lane)
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      tc[i] = (epi_tanh && lane < K4) ? mtd::ld_stream4(epi_tanh + roff[i] + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
     for (int c = lane; c < K4; c += 32) {
       float4 tn[RB];
       const bool more = epi_tanh && (c + 32 < K4);
 #pragma unroll
-      for (int i = 0; i < RB; ++i)
-        tn[i] = (more && r0 + i < M) ? mtd::ld_stream4(epi_tanh + (r0 + i) * K + 4 * (c + 32))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < RB; ++i) tn[i] = more ? mtd::ld_stream4(epi_tanh + roff[i] + 4 * (c + 32)) : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 o[RB];
 #pragma unroll
       for (int i = 0; i < RB; ++i) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* wp = Ws + c * NS;
 #pragma unroll
-      for (int n = 0; n < NP; ++n) {
-        if (n < N) {
-          const float4 w = Ws[n * K4 + c];
+      for (int n = 0; n < N; ++n) {
+        const float4 w = wp[n];
 #pragma unroll
-          for (int i = 0; i < RB; ++i) {
-            o[i].x = fmaf(dz[i][n], w.x, o[i].x);
-            o[i].y = fmaf(dz[i][n], w.y, o[i].y);
-            o[i].z = fmaf(dz[i][n], w.z, o[i].z);
-            o[i].w = fmaf(dz[i][n], w.w, o[i].w);
-          }
+        for (int i = 0; i < RB; ++i) {
+          o[i].x = fmaf(dz[i][n], w.x, o[i].x);
+          o[i].y = fmaf(dz[i][n], w.y, o[i].y);
+          o[i].z = fmaf(dz[i][n], w.z, o[i].z);
+          o[i].w = fmaf(dz[i][n], w.w, o[i].w);
         }
       }
 #pragma unroll
       for (int i = 0; i < RB; ++i) {
-        if (r0 + i < M) {
+        if (r0 + i < M) {                  // warp-uniform
           float4 v = o[i];
           if (epi_tanh) {
             const float4 t = tc[i];
@@ -168,7 +191,7 @@ __global__ void __launch_bounds__(THREADS) skinny_dx_kernel(float* __restrict__ 
             v.z = __fmul_rn(v.z, __fsub_rn(1.f, __fmul_rn(t.z, t.z)));
             v.w = __fmul_rn(v.w, __fsub_rn(1.f, __fmul_rn(t.w, t.w)));
           }
-          mtd::st4(dX + (r0 + i) * K + 4 * c, v);
+          mtd::st4(dX + roff[i] + 4 * c, v);
         }
       }
 #pragma unroll
@@ -317,30 +340,43 @@ __global__ void __launch_bounds__(THREADS) skinny_dw_ring_kernel(float* __restri
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int NP>
+constexpr size_t SMEM_OPTIN = 232448;      // 227 KB per CTA
+
+inline size_t skinny_w_bytes(long long n, long long k) { return (size_t)(n | 1) * (size_t)k * 4; }
+
+template <int N>
 int run_fwd(const GemmArgs& a, long long ldx, long long ldw) {
-  const size_t smem = (size_t)a.N * a.K * 4;
+  const size_t smem = skinny_w_bytes(N, a.K);
   const int grid = (int)std::min<long long>(g().sm_count, ceil_div(a.M, (THREADS / 32) * RB));
-  auto kern = skinny_fwd_kernel<NP>;
+  auto kern = skinny_fwd_kernel<N>;
   static bool set = false;
-  if (!set) { MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_MAX)); set = true; }
-  kern<<<grid, THREADS, smem, g().stream>>>(a.C, a.A, a.B, a.bias, a.M, (int)a.N, a.K, ldx, ldw, a.act);
+  if (!set) { MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_OPTIN)); set = true; }
+  kern<<<grid, THREADS, smem, g().stream>>>(a.C, a.A, a.B, a.bias, a.M, a.K, ldx, ldw, a.act);
   MT_LAUNCHED();
   return MT_OK;
 }
 
-template <int NP>
+template <int N>
 int run_dx(const GemmArgs& a, long long ldz, long long ldw) {
   // GEMM view: M x N_out(=a.N, the wide K of the layer) with reduction a.K (= the layer's tiny N)
-  const size_t smem = (size_t)a.K * a.N * 4;
-  auto kern = skinny_dx_kernel<NP>;
+  const size_t smem = skinny_w_bytes(N, a.N);
+  auto kern = skinny_dx_kernel<N>;
   static bool set = false;
-  if (!set) { MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_W_MAX)); set = true; }
+  if (!set) { MT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_OPTIN)); set = true; }
   const int grid = (int)std::min<long long>(g().sm_count, ceil_div(a.M, (THREADS / 32) * RB));
-  kern<<<grid, THREADS, smem, g().stream>>>(a.C, a.A, a.B, a.epi_tanh, a.M, (int)a.K, a.N, ldz, ldw);
+  kern<<<grid, THREADS, smem, g().stream>>>(a.C, a.A, a.B, a.epi_tanh, a.M, a.N, ldz, ldw);
   MT_LAUNCHED();
   return MT_OK;
 }
+
+// exact-N dispatch (1..16)
+#define MT_BY_N(n, CALL)                                                                                               \
+  switch (n) {                                                                                                         \
+    case 1: return CALL(1); case 2: return CALL(2); case 3: return CALL(3); case 4: return CALL(4);                    \
+    case 5: return CALL(5); case 6: return CALL(6); case 7: return CALL(7); case 8: return CALL(8);                    \
+    case 9: return CALL(9); case 10: return CALL(10); case 11: return CALL(11); case 12: return CALL(12);              \
+    case 13: return CALL(13); case 14: return CALL(14); case 15: return CALL(15); default: return CALL(16);            \
+  }
 
 template <int NP>
 int run_dw(const GemmArgs& a, long long ldz, long long ldx) {
@@ -402,18 +438,22 @@ int gemm_skinny_try(const GemmArgs& a) {
   // ---- forward shape: tiny N, A row-major [M,K], B(k,n) = W[n*ldw + k]
   if (a.N <= 16 && a.N >= 1 && a.M >= 256 && a.K >= 128 && a.a_sk == 1 && a.b_sk == 1 && !a.accumulate && !a.epi_tanh) {
     const long long ldx = a.a_sm, ldw = a.b_sn;
-    if (a.K % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0 && al16(a.A) && al16(a.B) && a.N * a.K * 4 <= SMEM_W_MAX)
-      return by_np(a.N, [&] { return run_fwd<4>(a, ldx, ldw); }, [&] { return run_fwd<8>(a, ldx, ldw); },
-                   [&] { return run_fwd<12>(a, ldx, ldw); }, [&] { return run_fwd<16>(a, ldx, ldw); });
+    if (a.K % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0 && al16(a.A) && al16(a.B) && skinny_w_bytes(a.N, a.K) <= SMEM_OPTIN) {
+#define MT_FWD(NN) run_fwd<NN>(a, ldx, ldw)
+      MT_BY_N(a.N, MT_FWD)
+#undef MT_FWD
+    }
   }
   // ---- dX shape: tiny reduction, A row-major [M,Kr], B(k,n) = W[k*ldw + n], wide output
   if (a.K <= 16 && a.K >= 1 && a.M >= 256 && a.N >= 128 && a.a_sk == 1 && a.b_sn == 1 && !a.accumulate && !a.bias &&
       a.act == MT_ACT_NONE) {
     const long long ldz = a.a_sm, ldw = a.b_sk;
     if (a.N % 4 == 0 && ldw % 4 == 0 && al16(a.B) && al16(a.C) && (!a.epi_tanh || al16(a.epi_tanh)) &&
-        a.K * a.N * 4 <= SMEM_W_MAX)
-      return by_np(a.K, [&] { return run_dx<4>(a, ldz, ldw); }, [&] { return run_dx<8>(a, ldz, ldw); },
-                   [&] { return run_dx<12>(a, ldz, ldw); }, [&] { return run_dx<16>(a, ldz, ldw); });
+        skinny_w_bytes(a.K, a.N) <= SMEM_OPTIN) {
+#define MT_DX(NN) run_dx<NN>(a, ldz, ldw)
+      MT_BY_N(a.K, MT_DX)
+#undef MT_DX
+    }
   }
   // ---- dW shape: tiny M, A(m,k) = dZ[k*ldz + m], B(k,n) = X[k*ldx + n], long reduction
   if (a.M <= 16 && a.M >= 1 && a.N >= 128 && a.K >= 1024 && a.a_sm == 1 && a.b_sn == 1 && !a.bias && a.act == MT_ACT_NONE &&

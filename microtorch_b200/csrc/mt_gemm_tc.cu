@@ -478,9 +478,12 @@ __device__ __forceinline__ void convert_tile_mix_mn(const uint8_t* raw_b, uint8_
     }
   }
 }
-// backward prologue: z = g * (1 - y^2) replaces the raw tile (the MMA truncates it to hi itself), lo(z) -> lo ring
+// backward prologue: z = g * (1 - y^2) replaces the raw tile (the MMA truncates it to hi itself), lo(z) -> lo ring.
+// `centred` = the centred remainder of split4_centered (the epilogue then scales by S); it must match what convert_tile
+// does to the B operand of the same launch (write_hi = 0: centred, write_hi = 1: plain).
 template <int VECS>
-__device__ __forceinline__ void convert_tile_prologue(uint8_t* raw_b, const uint8_t* y_b, uint8_t* lo_b, int ct) {
+__device__ __forceinline__ void convert_tile_prologue(uint8_t* raw_b, const uint8_t* y_b, uint8_t* lo_b, int ct,
+                                                      bool centred) {
   constexpr int PER = VECS / 128;
   constexpr int U = PER < 4 ? PER : 4;
   float4* raw = reinterpret_cast<float4*>(raw_b);
@@ -502,7 +505,8 @@ __device__ __forceinline__ void convert_tile_prologue(uint8_t* raw_b, const uint
       z.z = __fmul_rn(g[u].z, __fsub_rn(1.f, __fmul_rn(y[u].z, y[u].z)));
       z.w = __fmul_rn(g[u].w, __fsub_rn(1.f, __fmul_rn(y[u].w, y[u].w)));
       g[u] = z;
-      split4<false>(z, hi, y[u]);            // y[u] now holds lo(z)
+      if (centred) y[u] = split4_centered(z);   // y[u] now holds lo(z): same split as the B operand gets (convert_tile)
+      else split4<false>(z, hi, y[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -740,7 +744,7 @@ gemm_splitfp32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               if (B_MN) convert_tile_mix_mn<C::BN_LOCAL, 192>(sb, sb_lo, sb_lo + C::B_TILE / 2, ct);
               else convert_tile_mix_k<C::B_TILE / 16, 192>(sb, sb_lo, sb_lo + C::B_TILE / 2, ct);
             } else {
-            if (PRO) convert_tile_prologue<C::A_TILE / 16>(sa, sy, sa_lo, ct);
+            if (PRO) convert_tile_prologue<C::A_TILE / 16>(sa, sy, sa_lo, ct, !p.write_hi);
             else if (p.write_hi) convert_tile<C::A_TILE / 16, true>(sa, sa_lo, ct);
             else convert_tile<C::A_TILE / 16, false>(sa, sa_lo, ct);
             if (p.write_hi) convert_tile<C::B_TILE / 16, true>(sb, sb_lo, ct);
@@ -799,7 +803,7 @@ gemm_splitfp32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
       }
       // ---- tile epilogue: (mix-mode scale), bias, tanh, (accumulate), store.  One row per thread, 128 B per 32 columns.
-      const bool mix_scale = !PRO && (p.mix || !p.write_hi);   // centred split: accumulator scaled by S
+      const bool mix_scale = p.mix || !p.write_hi;   // centred split (every mode but write_hi): accumulator scaled by S
       const long long row = m0 + quad * 32 + lane;
       if (row < p.M) {
         float* crow = p.C + (long long)work_split(w) * p.M * p.N + row * p.N;   // split partials are stacked
@@ -889,7 +893,7 @@ static int ensure_debug_word() {
 }
 
 // per-launch event timing for the bench roofline (mt_prof_*)
-struct ProfRec { cudaEvent_t a, b; double flops; };
+struct ProfRec { cudaEvent_t a, b; double flops; double unit_flops; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_prof_pool;
@@ -908,11 +912,14 @@ static int g_dbg_flags = 0;   // Params::dbg
 static int g_splitk = 1;      // allow split-K for badly quantised tile counts
 static int g_lo_stages = 3;   // lo ring depth; the raw ring gets whatever else fits (or g_raw_stages if > 0)
 static int g_raw_stages = 0;
-static int g_fwd_mix = -1, g_fwd_chunk_kb = -1;   // >= 0: override mix / chunk_kb for GEMMs flagged `forward`
+static int g_fwd_mix = 0, g_fwd_chunk_kb = 4;     // >= 0: override mix / chunk_kb for GEMMs flagged `forward`; the default is
+                                                  // precision level 1 ("higher", see mt_gemm_set_precision)
 static int g_mix = 1;         // 1 (default): hi.hi on TF32, the two first-order corrections as BF16 products; 0: 3xTF32
 static int g_group_n = 0;     // tile order: 0 = choose per problem (see launch), > 0 = that many n-blocks per column group,
                               // < 0 = plain row-major order (all n-blocks in one group)
 static int g_hints = 6;       // bit 0: A loads evict_first, bit 1: streaming C stores, bit 2: B loads evict_last (see launch)
+static int g_max_units = 0;   // > 0: cap the persistent grid at this many units (CTAs or CTA pairs): leaves SMs free for a
+                              // concurrent collective kernel (experiment knob, tools/dp_ab.py)
 static int g_pair = 1;        // 1: CTA pairs (cta_group::2) for N > 128 when the shape allows; 0: single CTAs only
 
 template <int BN, bool A_MN, bool B_MN, int NCTA, bool PRO>
@@ -965,7 +972,8 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
   // split-K when the tile count quantises badly over the 148/NCTA persistent units (dW: 256 tiles on 74 pairs = 4
   // waves at 86 %): pick the smallest S <= 8 whose wave efficiency reaches 95 %, keeping >= 64 k-blocks per split
   const long long tiles = (long long)p.m_blocks * p.n_blocks;
-  const long long unit_count = g().sm_count / NCTA;
+  long long unit_count = g().sm_count / NCTA;
+  if (g_max_units > 0) unit_count = std::min<long long>(unit_count, std::max(1, g_max_units * 2 / NCTA));
   int S = 1;
   if (g_splitk && tiles < 8 * unit_count) {
     double best = 0.0;
@@ -1036,6 +1044,8 @@ static int launch(const GemmArgs& a, long long lda, long long ldb) {
     rec.a = prof_event();
     rec.b = prof_event();
     rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
+    // bf16-rate units per logical multiply-add: a TF32 product costs 2, a BF16 product 1 (mix: 2 + 1 + 1, all-TF32: 6)
+    rec.unit_flops = rec.flops * (p.mix ? 4.0 : 6.0);
     cudaEventRecord(rec.a, g().stream);
   }
   cudaLaunchConfig_t cfg{};
@@ -1133,29 +1143,40 @@ MT_API int mt_prof_reset(void) {
   tc::g_prof.clear();
   return MT_OK;
 }
-MT_API int mt_prof_gemm(uint64_t* launches, double* ms_total, double* flops_total) {
+static int prof_totals(uint64_t* launches, double* ms_total, double* flops_total, double* unit_flops_total) {
   MT_REQUIRE_INIT();
   MT_CUDA(cudaStreamSynchronize(g().stream));
-  double ms = 0.0, fl = 0.0;
+  double ms = 0.0, fl = 0.0, ufl = 0.0;
   for (auto& r : tc::g_prof) {
     float t = 0.f;
     MT_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
     ms += t;
     fl += r.flops;
+    ufl += r.unit_flops;
   }
   if (launches) *launches = tc::g_prof.size();
   if (ms_total) *ms_total = ms;
   if (flops_total) *flops_total = fl;
+  if (unit_flops_total) *unit_flops_total = ufl;
   return MT_OK;
+}
+MT_API int mt_prof_gemm(uint64_t* launches, double* ms_total, double* flops_total) {
+  return prof_totals(launches, ms_total, flops_total, nullptr);
+}
+MT_API int mt_prof_gemm_units(uint64_t* launches, double* ms_total, double* flops_total, double* unit_flops_total) {
+  return prof_totals(launches, ms_total, flops_total, unit_flops_total);
 }
 
 // Precision policy of the tensor-core GEMMs (public: mt_gemm_set_precision in the header).  Per-GEMM error against
 // float64 (4096^3, rms relative; tests/gemm_accuracy.py, profiles/r02_gemm_accuracy.jsonl) and what it costs:
-//   0 "high"    (default) TF32 hi.hi + two BF16 corrections, centred remainders, TMEM chunks of K = 256:  1.4e-6
-//   1 "higher"  forward GEMMs with all three products on TF32 and chunks of K = 128, backward as "high":  9.0e-7 fwd
+//   0 "high"    TF32 hi.hi + two BF16 corrections, centred remainders, TMEM chunks of K = 256:            1.4e-6
+//               (the fast mode: opt-in, like TF32 in torch)
+//   1 "higher"  (DEFAULT) forward GEMMs as the north_star's 3xTF32 - all three products on TF32 - with chunks of
+//               K = 128; the backward GEMMs (dW, dX) as "high":                                           9.0e-7 fwd
 //               (a deep, high-gain net amplifies FORWARD rounding ~100x into its gradients; backward hardly matters:
 //               config #5 at full width sits 1.3e-4 / 7.5e-5 / 5.3e-5 from the NumPy oracle at levels 0 / 1 / 2 - the
-//               oracle itself is 4e-5 from float64 there);                                  config #2 step +10 %
+//               oracle itself is 4e-5 from float64 there).  Level 1 is the cheapest level that keeps EVERY BASELINE
+//               config inside the north_star's 1e-4 of the oracle end to end;           config #2 step +10-12 % over "high"
 //   2 "highest" all-TF32 split, chunks of K = 64, everywhere:  4.8e-7 (NumPy / OpenBLAS SGEMM: 3.7e-7)    step +40 %
 MT_API int mt_gemm_set_precision(int level) {
   MT_CHECK_ARG(level >= 0 && level <= 2, "mt_gemm_set_precision: level must be 0 (high), 1 (higher) or 2 (highest)");
@@ -1213,6 +1234,11 @@ extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_chunk_kb(in
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_fwd(int mix, int chunk_kb) {
   tc::g_fwd_mix = mix;
   tc::g_fwd_chunk_kb = chunk_kb;
+  return MT_OK;
+}
+//   max_units: cap of the persistent grid in CTA PAIRS (single-CTA kernels get twice as many CTAs); 0 = every SM.
+extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_max_units(int v) {
+  tc::g_max_units = v < 0 ? 0 : v;
   return MT_OK;
 }
 extern "C" __attribute__((visibility("default"))) int mt_gemm_tc_set_mix(int v) {

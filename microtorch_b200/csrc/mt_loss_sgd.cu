@@ -20,6 +20,19 @@ constexpr int THREADS = 256;
 
 using mtd::loss_elem;
 
+template <int KIND, bool LEAN>
+__device__ __forceinline__ void loss_vec4(const float4 p, const float4 t, float scale, float4& g, float& a0, float& a1,
+                                          float& a2, float& a3) {
+  float v;
+  loss_elem<KIND, LEAN>(p.x, t.x, scale, v, g.x); a0 += v;
+  loss_elem<KIND, LEAN>(p.y, t.y, scale, v, g.y); a1 += v;
+  loss_elem<KIND, LEAN>(p.z, t.z, scale, v, g.z); a2 += v;
+  loss_elem<KIND, LEAN>(p.w, t.w, scale, v, g.w); a3 += v;
+}
+__device__ __forceinline__ bool lean4(const float4 p) {
+  return mtd::bce_lean_ok(p.x) && mtd::bce_lean_ok(p.y) && mtd::bce_lean_ok(p.z) && mtd::bce_lean_ok(p.w);
+}
+
 template <int KIND, bool WRITE_GRAD>
 __global__ void __launch_bounds__(THREADS) loss_kernel(float* __restrict__ loss_out, float* __restrict__ dpred,
                                                        const float* __restrict__ pred, const float* __restrict__ target,
@@ -36,15 +49,13 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(float* __restrict__ loss_
     float4 p0 = mtd::ld_stream4(pred + 4 * i), t0 = mtd::ld_stream4(target + 4 * i);
     float4 p1 = mtd::ld_stream4(pred + 4 * (i + stride)), t1 = mtd::ld_stream4(target + 4 * (i + stride));
     float4 g0, g1;
-    float v;
-    loss_elem<KIND>(p0.x, t0.x, scale, v, g0.x); acc0 += v;
-    loss_elem<KIND>(p0.y, t0.y, scale, v, g0.y); acc1 += v;
-    loss_elem<KIND>(p0.z, t0.z, scale, v, g0.z); acc2 += v;
-    loss_elem<KIND>(p0.w, t0.w, scale, v, g0.w); acc3 += v;
-    loss_elem<KIND>(p1.x, t1.x, scale, v, g1.x); acc0 += v;
-    loss_elem<KIND>(p1.y, t1.y, scale, v, g1.y); acc1 += v;
-    loss_elem<KIND>(p1.z, t1.z, scale, v, g1.z); acc2 += v;
-    loss_elem<KIND>(p1.w, t1.w, scale, v, g1.w); acc3 += v;
+    if (KIND == MT_LOSS_BCE && lean4(p0) && lean4(p1)) {
+      loss_vec4<KIND, true>(p0, t0, scale, g0, acc0, acc1, acc2, acc3);
+      loss_vec4<KIND, true>(p1, t1, scale, g1, acc0, acc1, acc2, acc3);
+    } else {
+      loss_vec4<KIND, false>(p0, t0, scale, g0, acc0, acc1, acc2, acc3);
+      loss_vec4<KIND, false>(p1, t1, scale, g1, acc0, acc1, acc2, acc3);
+    }
     if (WRITE_GRAD) {
       mtd::st4(dpred + 4 * i, g0);
       mtd::st4(dpred + 4 * (i + stride), g1);
@@ -52,11 +63,7 @@ __global__ void __launch_bounds__(THREADS) loss_kernel(float* __restrict__ loss_
   }
   for (; i < n4; i += stride) {
     float4 p0 = mtd::ld_stream4(pred + 4 * i), t0 = mtd::ld_stream4(target + 4 * i), g0;
-    float v;
-    loss_elem<KIND>(p0.x, t0.x, scale, v, g0.x); acc0 += v;
-    loss_elem<KIND>(p0.y, t0.y, scale, v, g0.y); acc1 += v;
-    loss_elem<KIND>(p0.z, t0.z, scale, v, g0.z); acc2 += v;
-    loss_elem<KIND>(p0.w, t0.w, scale, v, g0.w); acc3 += v;
+    loss_vec4<KIND, false>(p0, t0, scale, g0, acc0, acc1, acc2, acc3);
     if (WRITE_GRAD) mtd::st4(dpred + 4 * i, g0);
   }
   for (size_t j = (n4 << 2) + tid; j < n; j += stride) {

@@ -282,7 +282,7 @@ int reduce_rows(float* out, const float* x, long long outer, long long red, cons
 }
 
 int reduce_cols(float* out, const float* x, long long outer, long long red, long long inner, const float* w,
-                long long so, long long sr, long long si) {
+                long long so, long long sr, long long si, bool may_split = true) {
   cudaStream_t st = g().stream;
   const int sms = g().sm_count;
   const bool vec = inner % 4 == 0 && aligned16(x) && aligned16(out) &&
@@ -304,7 +304,7 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
   const long long tiles = ceil_div(vcols, (long long)TXr);
   const long long oz = std::min<long long>(outer, 65535);
   long long splits = 1;
-  if (tiles * oz < 4LL * sms) {
+  if (may_split && tiles * oz < 4LL * sms) {
     // fill the machine (4 CTAs per SM) but leave every row lane at least ~8 rows of work
     splits = std::min<long long>(ceil_div(4LL * sms, tiles * oz), ceil_div(red, (long long)TYr * 8));
     if (splits < 1) splits = 1;
@@ -329,7 +329,9 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
 #undef MT_COLS
   MT_LAUNCHED();
   if (splits > 1) {
-    int rc = reduce_cols(out, partial, outer, splits, inner, nullptr, 0, 0, 0);
+    // the fold of the partials is ONE more launch (it used to split again: three launches for a 2^26-element
+    // sum(axis=0), 10 us of launch latency on a 43 us kernel)
+    int rc = reduce_cols(out, partial, outer, splits, inner, nullptr, 0, 0, 0, false);
     return rc;
   }
   return MT_OK;

@@ -25,7 +25,7 @@ int8 = _np.int8
 
 
 def set_float32_matmul_precision(level: str) -> None:
-    """"high" (default) | "higher" | "highest": fp32 emulation level of the tensor-core GEMMs (see _capi)."""
+    """"high" | "higher" (default) | "highest": fp32 emulation level of the tensor-core GEMMs (see _capi)."""
     _capi.set_float32_matmul_precision(level)
 
 

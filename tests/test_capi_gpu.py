@@ -327,6 +327,7 @@ def test_tensor_core_split_modes_agree(lib, M, N, K):
     (3xTF32) and float64: forward and both backward GEMMs, every operand-major combination.  Both stay at fp32 level
     (1e-5 here; the contract is 1e-4), so they also agree with each other to that level."""
     lib.mt_gemm_tc_set_mix.argtypes = [C.c_int]
+    lib.mt_gemm_tc_set_fwd.argtypes = [C.c_int, C.c_int]
     rng = np.random.default_rng(M + N + K)
     X = np.tanh(rng.standard_normal((M, K))).astype(np.float32)
     W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
@@ -338,6 +339,7 @@ def test_tensor_core_split_modes_agree(lib, M, N, K):
     dXr = dZ.astype(np.float64) @ W.astype(np.float64)
     outs = {}
     lib.mt_gemm_set_engine(1)
+    lib.mt_gemm_tc_set_fwd(-1, -1)            # the forward GEMM follows `mix` too (by default it is always 3xTF32)
     try:
         for mix in (1, 0):
             lib.mt_gemm_tc_set_mix(mix)
@@ -348,7 +350,7 @@ def test_tensor_core_split_modes_agree(lib, M, N, K):
             for got, ref in zip(outs[mix], (Yr, dWr, dXr)):
                 assert gemm_err(got, ref) < 1e-5
     finally:
-        lib.mt_gemm_tc_set_mix(1)
+        lib.mt_gemm_set_precision(1)          # back to the library default
         lib.mt_gemm_set_engine(-1)
     for a, bb in zip(outs[1], outs[0]):
         assert gemm_err(a, bb.astype(np.float64)) < 1e-5

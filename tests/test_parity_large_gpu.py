@@ -170,10 +170,10 @@ def test_c5_full_width_one_step_vs_oracle(mt):
     This stack (gain ~3.7 per layer with the reference's uniform(-1,1)*0.1 init) amplifies FORWARD rounding about 100x
     into every gradient: the NumPy oracle itself sits 4e-5 (norm-wise) from a float64 evaluation of the same step
     (profiles/r02_gemm_accuracy.jsonl).  Per GEMM every precision level is >= 70x inside the 1e-4 tolerance; end to end:
-      "highest" (all-TF32 split, SGEMM-class)   must meet the north_star 1e-4 against the oracle  (measured 5.3e-5)
-      "higher"  (precise forward GEMMs)         must meet it too                                  (measured 7.5e-5)
-      "high"    (default, fastest)              measured 1.27e-4 against the oracle, 1.26e-4 against float64: asserted
-                <= 2e-4 here, and <= 1e-4 LAYER BY LAYER when each layer is fed the oracle's own activations."""
+      "higher"  (the DEFAULT: 3xTF32 forward GEMMs)  must meet the north_star 1e-4 against the oracle  (measured 7.5e-5)
+      "highest" (3xTF32 everywhere, SGEMM-class)     must meet it too                                  (measured 5.3e-5)
+      "high"    (the opt-in fast mode)               measured 1.27e-4 against the oracle, 1.26e-4 against float64:
+                asserted <= 2e-4 here - which is why it is not the default."""
     import ctypes as C
     from oracle import workloads as OW
     from microtorch_b200 import _capi
@@ -184,8 +184,9 @@ def test_c5_full_width_one_step_vs_oracle(mt):
     oracle_vs_truth = max(gemm_close(ref["grads"][2 * i], truth[i], tol=1.0) for i in range(8))
     measured = {}
     try:
-        for level, tol in (("highest", 1e-4), ("higher", 1e-4), ("high", 2e-4)):
-            _capi.set_float32_matmul_precision(level)
+        for level, tol in ((None, 1e-4), ("highest", 1e-4), ("high", 2e-4)):
+            if level is not None:                      # None = whatever the library starts with: must be "higher"
+                _capi.set_float32_matmul_precision(level)
             model, x, t = W.setup(wl, mt.Linear, mt.Tanh, mt.Sequential)
             X, T = mt.Tensor(x, device="cuda"), mt.Tensor(t, device="cuda")
             loss = train_step(model, mt.losses["mse"](), mt.SGD(model.parameters, lr=wl.lr), X, T)
@@ -204,10 +205,10 @@ def test_c5_full_width_one_step_vs_oracle(mt):
             mt.lib.mt_gemm_last_engine(C.byref(engine))
             assert engine.value == 1, "the 4096-wide layers must run on the tcgen05 engine"
     finally:
-        _capi.set_float32_matmul_precision("high")
+        _capi.set_float32_matmul_precision("higher")
     print("c5 full width: max dW error vs oracle / vs float64:", measured, "oracle vs float64:", oracle_vs_truth)
-    # the default level is no further from the TRUTH than 4x the oracle's own distance
-    assert measured["high"][1] <= 4.0 * oracle_vs_truth + 1e-5, (measured, oracle_vs_truth)
+    # the default level is no further from the TRUTH than 2.5x the oracle's own distance
+    assert measured[None][1] <= 2.5 * oracle_vs_truth + 1e-5, (measured, oracle_vs_truth)
 
 
 def test_c5_full_width_layer_by_layer_default_precision(mt):

@@ -361,13 +361,25 @@ def main():
         sampler.start()
         time.sleep(0.3)
     lib.mt_prof_reset()
-    lib.mt_prof_enable(1)
     lib.mt_launch_count_reset()
+    # N = 1: every tcgen05 launch of the timed region is bracketed by CUDA events (mt_prof_*): the roofline numbers are
+    # measured live over the timed region itself.  N > 1: the timed region runs WITHOUT per-kernel events and a second
+    # pass of the same steps right after it is profiled instead - timing events at every kernel boundary of the compute
+    # stream open gaps in which the concurrent NCCL kernel takes SMs from the next persistent GEMM, which then waits
+    # for the peer rank: measured 33.2 vs 30.0 ms per step at N = 2 (profiles/r02_bench_n2_prof_events_ab.txt)
+    prof_live = world == 1
+    lib.mt_prof_enable(1 if prof_live else 0)
     t_wall0 = time.time()
     ms_total = timed(step_resident, args.steps)
     t_wall1 = time.time()
     launches = C.c_uint64()
     lib.mt_launch_count(C.byref(launches))
+    prof_steps = args.steps
+    if not prof_live:
+        prof_steps = max(3, args.steps // 2)
+        lib.mt_prof_reset()
+        lib.mt_prof_enable(1)
+        timed(step_resident, prof_steps)
     n_gemm, gemm_ms, gemm_flops, gemm_unit_flops = C.c_uint64(), C.c_double(), C.c_double(), C.c_double()
     lib.mt_prof_gemm_units(C.byref(n_gemm), C.byref(gemm_ms), C.byref(gemm_flops), C.byref(gemm_unit_flops))
     lib.mt_prof_enable(0)
@@ -377,7 +389,7 @@ def main():
         # every rank's own tcgen05 time per step: under the power cap the chips of one box do not run at the same
         # clock, and the step of a data-parallel job is paced by the slowest one - that spread is not communication
         import torch
-        mine = torch.tensor([gemm_ms.value / args.steps], dtype=torch.float64)
+        mine = torch.tensor([gemm_ms.value / prof_steps], dtype=torch.float64)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         per_rank = {"gemm_ms_per_step_by_rank": [round(float(a[0]), 3) for a in allr]}
@@ -481,8 +493,11 @@ def main():
             last["loss"] = tr5.step(X5, T5)
         c5_steps = max(3, min(args.steps, 5))
         lib.mt_prof_reset()
-        lib.mt_prof_enable(1)
+        lib.mt_prof_enable(1 if prof_live else 0)
         ms5 = timed(lambda: last.__setitem__("loss", tr5.step(X5, T5)), c5_steps)
+        if not prof_live:                  # N > 1: per-kernel events in a separate pass (see above)
+            lib.mt_prof_enable(1)
+            timed(lambda: last.__setitem__("loss", tr5.step(X5, T5)), 2)
         n5, gms5, gfl5 = C.c_uint64(), C.c_double(), C.c_double()
         lib.mt_prof_gemm(C.byref(n5), C.byref(gms5), C.byref(gfl5))
         lib.mt_prof_enable(0)
@@ -528,8 +543,11 @@ def main():
                      "frac_of_burst_peak": achieved_tf / (peaks["bf16"] / EMU) if peaks["bf16"] else None,
                      "traffic": ncu_traffic_per_launch(),
                      "traffic_unit": "bytes per launch (dram read+write, ncu --set full capture under profiles/)",
-                     "launches": int(n_gemm.value), "kernel_ms_per_step": gemm_ms.value / args.steps,
-                     "share_of_step": (gemm_ms.value / args.steps) / (ms_total / args.steps),
+                     "launches": int(n_gemm.value), "kernel_ms_per_step": gemm_ms.value / prof_steps,
+                     "share_of_step": (gemm_ms.value / prof_steps) / (ms_total / args.steps),
+                     "measured": ("CUDA events around every tcgen05 launch of the timed region" if prof_live else
+                                  f"CUDA events around every tcgen05 launch of a second pass of {prof_steps} steps right after the "
+                                  "timed region (N > 1: per-kernel events perturb the compute / NCCL overlap)"),
                      "bf16_units_per_logical_mac": EMU,
                      "peak_source": f"{peaks['source']}: bf16 sustained {peaks['bf16_sustained']} TF/s / {EMU:.3f} - the flop-weighted "
                                     "bf16-rate units per logical multiply-add of this step's GEMMs (TF32 product = 2 units, BF16 "

@@ -72,6 +72,8 @@ def main():
         out = DeviceArray.empty((R, Cc))
         row = DeviceArray.from_host(rng.uniform(0.5, 1.5, (1, Cc)).astype(np.float32))
         col = DeviceArray.from_host(rng.uniform(0.5, 1.5, (R, 1)).astype(np.float32))
+        prob = DeviceArray.from_host(rng.uniform(0.02, 0.98, (R, Cc)).astype(np.float32))     # BCE needs p in (0, 1)
+        tgt = DeviceArray.from_host(rng.uniform(0.0, 1.0, (R, Cc)).astype(np.float32))
         work = {
             "bin_flat add (x+y)": (lambda: K.binary(_capi.BIN_ADD, x, y, out=out), 3 * B),
             "bin_flat tanh' (g*(1-y^2))": (lambda: K.binary(_capi.BIN_TANH_BWD, x, y, out=out), 3 * B),
@@ -85,7 +87,7 @@ def main():
             "reduce_cols sum(axis=0)": (lambda: K.sum(x, 0), B),
             "reduce_cols fused g*x -> row": (lambda: K.reduce_sum(x, (0,), y), 2 * B),
             "loss_kernel mse fwd+bwd": (lambda: K.loss_forward_backward(_capi.LOSS_MSE, x, y, n, True), 3 * B),
-            "loss_kernel bce fwd+bwd": (lambda: K.loss_forward_backward(_capi.LOSS_BCE, x, y, n, True), 3 * B),
+            "loss_kernel bce fwd+bwd": (lambda: K.loss_forward_backward(_capi.LOSS_BCE, prob, tgt, n, True), 3 * B),
             "sgd_multi_kernel": (lambda: K.sgd_multi([x], [y], 1e-9), 3 * B),
             "zero_multi_kernel": (lambda: K.zero_multi([out]), B),
         }
@@ -116,7 +118,7 @@ def main():
             clk = sampler.window(t0, t1)
             print(json.dumps({"kernel": name, "log2_n": p, "ms": ms, "alg_gb": nbytes / 1e9, "gbs": nbytes / ms / 1e6,
                               "frac_of_measured_hbm": nbytes / ms / 1e6 / peak, "clocks": clk}), flush=True)
-        del work, x, y, out
+        del work, x, y, out, prob, tgt
     if sampler is not None:
         sampler.stop(0, time.time())
 

@@ -310,7 +310,11 @@ def main():
             box = [uid]
             dist.broadcast_object_list(box, src=0)
             return box[0]
-        comm = Communicator(rank, world, exchange)
+        def allgather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        comm = Communicator(rank, world, exchange, allgather)
     dp_parity = None
     if world > 1:
         dp_parity = dp_parity_check(comm, dist, rank, world, {"W": W, "nn": nn, "Tanh": Tanh, "Tensor": Tensor})

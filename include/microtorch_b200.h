@@ -280,6 +280,16 @@ int mt_mlp_fit_f32(const mt_mlp_desc* desc, const float* X, const float* T, int6
                    int has_pred_map, float pred_scale, float pred_shift, float lr, float loss_scale, int steps,
                    float* losses);
 
+/* ---------------------------------------------------------------- random ---------- */
+/* replaces: cupy.random.randn / cupy.random.uniform behind Tensor.randn / Tensor.uniform on device="cuda"
+ * (src/tensor/tensor.py:402-434).  A specified counter-based stream - Philox4x32-10, key = seed, block b = counter
+ * (b, 0), four words per block - so results are reproducible and checkable on the host (tests/test_rng_gpu.py);
+ * CuPy's own stream cannot be reproduced, parity with the reference is by distribution.  Each call consumes
+ * ceil(n / 4) blocks starting at `offset`; the caller keeps the offset.
+ *   uniform: out = low + (high - low) * ((x >> 8) + 0.5) * 2^-24        normal: Box-Muller on word pairs          */
+int mt_rng_uniform_f32(float* out, size_t n, unsigned long long seed, unsigned long long offset, float low, float high);
+int mt_rng_normal_f32(float* out, size_t n, unsigned long long seed, unsigned long long offset);
+
 /* ---------------------------------------------------------------- collective ------ */
 /* Data-parallel gradient exchange (no counterpart in the reference: new component,
  * SURVEY.md section 8(e)).  NCCL is dlopen()ed from `libnccl_path` (NULL = "libnccl.so.2"). */
@@ -296,6 +306,18 @@ int mt_allreduce_sum_f32(float* buf, size_t n);
  * behind it); the update itself is ordered after everything queued on the compute stream at the time of the call.
  * Without a communicator (world 1) it is just the deferred update.  Readers of `param` must follow mt_comm_wait(). */
 int mt_allreduce_sgd_f32(float* param, float* grad, size_t n, float lr);
+/* Peer-memory exchange (NVLink P2P through CUDA IPC; no NCCL in the data path): every rank owns an arena that its peers
+ * map; a finalised weight gradient is published, reduce-scattered + all-gathered in ONE pass of peer loads / stores with a
+ * fixed rank-order sum (bit-identical replicas), and applied (param -= lr * sum) - three small kernels on the communication
+ * stream, all waits bounded.  mt_p2p_create exports this rank's 64-byte IPC handle; mt_p2p_open takes all `world` handles
+ * in rank order.  `key` names the tensor identically on every rank.  MT_ERR_UNSUPPORTED = use mt_allreduce_sgd_f32.
+ * New component like the rest of this block (the reference has no distributed code).                                   */
+int mt_p2p_create(size_t arena_bytes, char* handle_out_64);
+int mt_p2p_open(int rank, int world, const char* handles_world_x_64);
+int mt_p2p_active(int* active);
+int mt_p2p_error(unsigned* code);
+int mt_p2p_allreduce_sgd_f32(float* param, float* grad, size_t n, float lr, unsigned long long key);
+int mt_p2p_destroy(void);
 /* make the compute stream wait for the communication stream; also polls ncclCommGetAsyncError (a dead peer aborts
  * the communicator and returns MT_ERR_NCCL instead of hanging)                                                   */
 int mt_comm_wait(void);

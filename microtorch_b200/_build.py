@@ -33,6 +33,8 @@ SOURCES = [
     "mt_linear.cu",
     "mt_mlp_small.cu",
     "mt_comm.cu",
+    "mt_p2p.cu",
+    "mt_rng.cu",
 ]
 
 NVCC_FLAGS = [

@@ -101,6 +101,14 @@ PROTOTYPES = {
     "mt_comm_world": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "mt_allreduce_sum_f32": [VP, C.c_size_t],
     "mt_allreduce_sgd_f32": [VP, VP, C.c_size_t, C.c_float],
+    "mt_rng_uniform_f32": [VP, C.c_size_t, C.c_ulonglong, C.c_ulonglong, C.c_float, C.c_float],
+    "mt_rng_normal_f32": [VP, C.c_size_t, C.c_ulonglong, C.c_ulonglong],
+    "mt_p2p_create": [C.c_size_t, C.c_char_p],
+    "mt_p2p_open": [C.c_int, C.c_int, C.c_char_p],
+    "mt_p2p_active": [C.POINTER(C.c_int)],
+    "mt_p2p_error": [C.POINTER(C.c_uint)],
+    "mt_p2p_allreduce_sgd_f32": [VP, VP, C.c_size_t, C.c_float, C.c_ulonglong],
+    "mt_p2p_destroy": [],
     "mt_comm_wait": [],
     "mt_comm_check": [],
     "mt_comm_destroy": [],

@@ -79,6 +79,44 @@ def wait_prefetch() -> None:
     _capi.check(_capi.lib().mt_prefetch_wait(), "mt_prefetch_wait")
 
 
+class random:                      # noqa: N801  (NumPy / CuPy name)
+    """Device generator behind Tensor.randn / Tensor.uniform on device="cuda" - where the reference calls
+    cupy.random.randn / cupy.random.uniform (src/tensor/tensor.py:402-434).  Philox4x32-10 keyed by `seed`; every call
+    consumes ceil(n / 4) blocks of the stream (mt_rng_*_f32 in the C header has the exact definition), so a seeded
+    program is reproducible.  Never seeded: the seed is drawn from NumPy's global generator at first use, so
+    `np.random.seed(k)` fixes the device stream too."""
+    _seed = None
+    _offset = 0
+
+    @classmethod
+    def seed(cls, seed=None) -> None:
+        cls._seed = None if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
+        cls._offset = 0
+
+    @classmethod
+    def _state(cls, n):
+        if cls._seed is None:
+            cls._seed = int(_np.random.randint(0, 2 ** 31 - 1)) | (int(_np.random.randint(0, 2 ** 31 - 1)) << 32)
+        off = cls._offset
+        cls._offset += (n + 3) // 4
+        return cls._seed, off
+
+    @classmethod
+    def randn(cls, *dims) -> DeviceArray:
+        out = DeviceArray.empty(tuple(int(d) for d in dims))
+        seed, off = cls._state(out.size)
+        _capi.check(_capi.lib().mt_rng_normal_f32(out.ptr, out.size, seed, off), "mt_rng_normal_f32")
+        return out
+
+    @classmethod
+    def uniform(cls, low=0.0, high=1.0, size=None) -> DeviceArray:
+        shape = () if size is None else ((int(size),) if _np.isscalar(size) else tuple(int(d) for d in size))
+        out = DeviceArray.empty(shape)
+        seed, off = cls._state(out.size)
+        _capi.check(_capi.lib().mt_rng_uniform_f32(out.ptr, out.size, seed, off, float(low), float(high)), "mt_rng_uniform_f32")
+        return out
+
+
 def zeros_like(x, dtype=None) -> DeviceArray:
     return DeviceArray.zeros(x.shape)
 

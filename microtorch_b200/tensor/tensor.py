@@ -368,18 +368,20 @@ class Tensor:
         return (f"Tensor(data={self.data}, requires_grad={self.requires_grad}, shape={self.shape}, "
                 f"dtype={self.dtype}, device={self.device})")
 
-    # ------------------------------------------------------------------ factories (host RNG, then upload)
+    # ------------------------------------------------------------------ factories: drawn on the tensor's own device,
+    # as the reference does (`_tensor(device).random...`, tensor.py:402-434): NumPy's generator on the CPU, the
+    # library's Philox stream (microtorch_b200.cuda.random) on CUDA.  Parameter init stays on the host (Q7: nn/param.py).
     @staticmethod
     def randn(dims: Dims = (), requires_grad=False, device: Device = Device.CPU) -> "Tensor":
         if type(dims) is int:
             dims = (dims,)
-        return Tensor(np.random.randn(*dims), requires_grad=requires_grad, device=device)
+        return Tensor(_tensor(device).random.randn(*dims), requires_grad=requires_grad, device=device)
 
     @staticmethod
     def uniform(low: float, high: float, dims: Dims = (), requires_grad=False, device: Device = Device.CPU) -> "Tensor":
         if type(dims) is int:
             dims = (dims,)
-        return Tensor(np.random.uniform(low, high, dims), requires_grad=requires_grad, device=device)
+        return Tensor(_tensor(device).random.uniform(low, high, dims), requires_grad=requires_grad, device=device)
 
     # ------------------------------------------------------------------ shape ops
     @from_op

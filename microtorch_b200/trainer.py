@@ -181,7 +181,12 @@ class Communicator:
     `exchange_id` moves the 128-byte NCCL unique id from rank 0 to everyone: any callable
     `bytes|None -> bytes` (torch.distributed broadcast over gloo in bench.py, a file in tests)."""
 
-    def __init__(self, rank: int, world: int, exchange_id: Callable[[Optional[bytes]], bytes]) -> None:
+    def __init__(self, rank: int, world: int, exchange_id: Callable[[Optional[bytes]], bytes],
+                 allgather: Optional[Callable[[bytes], list]] = None, peer_arena_bytes: Optional[int] = None) -> None:
+        """`allgather` (bytes -> list of every rank's bytes, in rank order) enables the peer-memory exchange
+        (csrc/mt_p2p.cu): every rank allocates an arena, the CUDA IPC handles are all-gathered, and weight gradients
+        are summed and applied through NVLink loads / stores instead of ncclAllReduce.  It is used only if EVERY rank
+        could map every peer; MICROTORCH_B200_P2P=0 keeps NCCL."""
         self.rank, self.world = rank, world
         self.lib = _capi.lib()
         _capi.require_device()
@@ -194,20 +199,56 @@ class Communicator:
             uid = buf.raw
         uid = exchange_id(uid)
         _capi.check(self.lib.mt_comm_init_rank(uid, rank, world), "mt_comm_init_rank")
+        self.p2p = False
+        self.p2p_fallbacks = 0
+        if allgather is not None and 2 <= world <= 8 and os.environ.get("MICROTORCH_B200_P2P", "1") != "0":
+            if peer_arena_bytes is None:
+                peer_arena_bytes = int(os.environ.get("MICROTORCH_B200_P2P_ARENA_MB", "4096")) << 20
+            handle = C.create_string_buffer(64)
+            ok = self.lib.mt_p2p_create(peer_arena_bytes, handle) == 0
+            handles = allgather(bytes([1 if ok else 0]) + handle.raw)
+            if all(len(h) == 65 and h[0] == 1 for h in handles):
+                ok = self.lib.mt_p2p_open(rank, world, b"".join(h[1:] for h in handles)) == 0
+            else:
+                ok = False
+            votes = allgather(bytes([1 if ok else 0]))
+            self.p2p = all(v == b"\x01" for v in votes)
+            if not self.p2p:
+                self.lib.mt_p2p_destroy()
 
     def allreduce_(self, arr) -> None:
         """In-place sum over ranks, asynchronous on the communication stream."""
         _capi.check(self.lib.mt_allreduce_sum_f32(arr.ptr, arr.size), "mt_allreduce_sum_f32")
 
-    def allreduce_sgd_(self, param, grad, lr: float) -> None:
-        """grad <- sum over ranks; param -= lr * grad - both on the communication stream (mt_allreduce_sgd_f32)."""
+    def allreduce_sgd_(self, param, grad, lr: float, key: Optional[int] = None) -> None:
+        """grad <- sum over ranks; param -= lr * grad - both on the communication stream.  With a peer arena and a `key`
+        (the same integer on every rank for the same parameter) the exchange goes through NVLink peer memory
+        (mt_p2p_allreduce_sgd_f32); tensors the arena cannot take, and communicators without one, use ncclAllReduce
+        (mt_allreduce_sgd_f32) - a decision every rank takes identically."""
+        if self.p2p and key is not None:
+            rc = self.lib.mt_p2p_allreduce_sgd_f32(param.ptr, grad.ptr, grad.size, float(lr), int(key))
+            if rc == 0:
+                param._host_value = None
+                return
+            if rc != _capi.ERR_UNSUPPORTED:
+                _capi.check(rc, "mt_p2p_allreduce_sgd_f32")
+            self.p2p_fallbacks += 1
         _capi.check(self.lib.mt_allreduce_sgd_f32(param.ptr, grad.ptr, grad.size, float(lr)), "mt_allreduce_sgd_f32")
         param._host_value = None
 
     def wait(self) -> None:
         _capi.check(self.lib.mt_comm_wait(), "mt_comm_wait")
+        if self.p2p:
+            code = C.c_uint(0)
+            self.lib.mt_p2p_error(C.byref(code))
+            if code.value:
+                raise RuntimeError(f"peer-memory exchange timed out: phase {code.value & 0xff}, waiting for rank "
+                                   f"{(code.value >> 8) & 0xff}, slot {code.value >> 16}")
 
     def close(self) -> None:
+        if self.p2p:
+            self.lib.mt_p2p_destroy()
+            self.p2p = False
         self.lib.mt_comm_destroy()
 
 
@@ -233,6 +274,8 @@ class GlooCommunicator:
 
 
 class DataParallelTrainer:
+    _created = 0
+
     def __init__(self, model: Module, loss_fn: Loss, lr: float, comm: Optional[Communicator] = None,
                  pred_map: Optional[Tuple[float, float]] = None, squeeze_dim: Optional[int] = None,
                  overlap: bool = True) -> None:
@@ -251,6 +294,13 @@ class DataParallelTrainer:
         self.steps = 0
         self.hook_order = []          # id(param) in the order the gradients became final (last step)
         self._updated = set()         # parameters already updated behind their all-reduce in this step
+        # names of the parameters for the peer-memory exchange: (trainer number) << 32 | index in model.parameters().
+        # Trainers with a communicator are created in the same order on every rank, so the keys agree across ranks.
+        self._trainer_no = 0
+        if comm is not None:
+            DataParallelTrainer._created += 1
+            self._trainer_no = DataParallelTrainer._created
+        self._keys = {}
 
     def _on_grad_final(self, param: Tensor) -> None:
         g = param._grad
@@ -268,7 +318,10 @@ class DataParallelTrainer:
             return
         fused_update = getattr(self.comm, "allreduce_sgd_", None)
         if fused_update is not None and param.device == Device.CUDA and param.data.is_dense and g.size == param.data.size:
-            fused_update(param.data, g, self.optimizer.lr)
+            if getattr(self.comm, "p2p", False):
+                fused_update(param.data, g, self.optimizer.lr, self._keys.get(id(param)))
+            else:
+                fused_update(param.data, g, self.optimizer.lr)
             self._updated.add(id(param))
         else:
             self.comm.allreduce_(g)
@@ -287,8 +340,10 @@ class DataParallelTrainer:
         loss = self.loss_fn(pred, target)
         if self.comm is not None and self.world > 1:
             # Parameter objects are replaced on the first forward (Q6): hook the current ones
-            for p in model.parameters():
+            self._keys = {}
+            for i, p in enumerate(model.parameters()):
                 p._grad_hook = self._on_grad_final
+                self._keys[id(p)] = (self._trainer_no << 32) | i
             self.hook_order = []
             self._updated = set()
         loss.backward()

@@ -30,20 +30,30 @@ def main():
         box = [uid]
         dist.broadcast_object_list(box, src=0)
         return box[0]
-    comm = Communicator(rank, world, exchange)
+    def allgather(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+    comm = Communicator(rank, world, exchange, allgather)
     tr = DataParallelTrainer(model, MSELoss(), wl.lr, comm)
     X, T = Tensor(x[rows], device="cuda"), Tensor(t[rows], device="cuda")
     losses = []
     for _ in range(3):
         losses.append(tr.global_loss(tr.step(X, T)))
     params = [p.data.get() for p in model.parameters()]
+    # replicas must be bit-identical after the exchange (the peer-memory path sums in a fixed rank order)
+    import hashlib
+    digests = [None] * world
+    dist.all_gather_object(digests, hashlib.sha256(b"".join(p.tobytes() for p in params)).hexdigest())
     if rank == 0:
         from oracle import workloads as OW
         ref = OW.run_steps(wl, 3)
         err = max(float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30)) for a, b in zip(params, ref["params"]))
         lerr = float(np.abs(np.array(losses) - ref["losses"]).max() / np.abs(ref["losses"]).max())
         print("DP_PARITY " + json.dumps({"world": world, "param_err": err, "loss_err": lerr, "losses": losses,
-                                         "exchanged_bytes": tr.exchanged_bytes}), flush=True)
+                                         "exchanged_bytes": tr.exchanged_bytes, "peer_memory": bool(comm.p2p),
+                                         "p2p_fallbacks": comm.p2p_fallbacks,
+                                         "replicas_bit_identical": len(set(digests)) == 1}), flush=True)
     dist.barrier()
     comm.close()
     dist.destroy_process_group()

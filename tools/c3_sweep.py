@@ -40,12 +40,16 @@ def main():
     e0, e1 = C.c_void_p(), C.c_void_p()
     lib.mt_event_create(C.byref(e0))
     lib.mt_event_create(C.byref(e1))
+    from bench import ClockSampler            # nvidia-smi clocks / throttle reasons sampled while each row runs
+    sampler = ClockSampler(0, period_ms=50)
+    sampler.start()
+    time.sleep(0.3)
 
     def timed(fn, iters):
         for _ in range(3):
             fn()
-        tot = 0.0
-        for _ in range(iters):
+        tot, reps, t0 = 0.0, 0, time.time()
+        while reps < iters or time.time() - t0 < 0.3:          # long enough for the clock sampler to see the row
             lib.mt_l2_flush()
             lib.mt_event_record(e0)
             fn()
@@ -54,7 +58,8 @@ def main():
             ms = C.c_float()
             lib.mt_event_elapsed_ms(e0, e1, C.byref(ms))
             tot += ms.value
-        return tot / iters
+            reps += 1
+        return tot / reps, sampler.window(t0, time.time())
 
     rng = np.random.default_rng(0)
     for p in range(args.min, args.max + 1, args.step):
@@ -127,13 +132,14 @@ def main():
         for name, (fn, nbytes) in work.items():
             if args.only and not any(k in name for k in args.only.split(',')):
                 continue
-            ms = timed(fn, args.iters)
+            ms, clk = timed(fn, args.iters)
             rec = {"workload": name, "log2_n": p, "ms": ms, "alg_gb": nbytes / 1e9, "gbs": nbytes / ms / 1e6,
-                   "frac_of_measured_hbm": nbytes / ms / 1e6 / peak}
+                   "frac_of_measured_hbm": nbytes / ms / 1e6 / peak, "clocks": clk}
             print(json.dumps(rec), flush=True)
         for gs in graphs:
             gs.close()
         del x, work
+    sampler.stop(0, time.time())
 
 
 if __name__ == "__main__":

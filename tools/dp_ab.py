@@ -63,7 +63,11 @@ def main():
         box = [uid]
         dist.broadcast_object_list(box, src=0)
         return box[0]
-    comm = Communicator(rank, world, exchange)
+    def allgather(b):
+        out = [None] * world
+        dist.all_gather_object(out, b)
+        return out
+    comm = Communicator(rank, world, exchange, allgather)
 
     def make(schedule):
         np.random.seed(wl.seed)

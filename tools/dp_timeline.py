@@ -59,7 +59,11 @@ def main():
             box = [uid]
             dist.broadcast_object_list(box, src=0)
             return box[0]
-        comm = Communicator(rank, world, exchange)
+        def allgather(b):
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        comm = Communicator(rank, world, exchange, allgather)
     trainer = DataParallelTrainer(model, CrossEntropyLoss() if wl.loss == "ce" else MSELoss(), wl.lr, comm, wl.pred_map,
                                   wl.squeeze_dim, overlap=not args.no_overlap)
     X, T = Tensor(x, device="cuda"), Tensor(t, device="cuda")

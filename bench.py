@@ -533,6 +533,9 @@ def main():
                    "per_gpu_batch": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
                    "l2": "inputs larger than L2 (activations 1 GiB per layer); no flush needed",
                    "matmul_precision": args.precision,
+                   "exchange": (None if comm is None else
+                                "NVLink peer memory: reduce-scatter + all-gather + SGD in the library's own kernels (mt_p2p.cu)"
+                                if getattr(comm, "p2p", False) else "ncclAllReduce + SGD on the communication stream (mt_comm.cu)"),
                    "gemm": "tcgen05 split-fp32, chunked TMEM accumulation: " +
                            {"high": "TF32 hi.hi + 2 BF16 corrections per k-slice in every GEMM",
                             "higher": "forward GEMMs 3xTF32, backward GEMMs TF32 hi.hi + 2 BF16 corrections",

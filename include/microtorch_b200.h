@@ -229,8 +229,8 @@ int mt_matmul_f32(float* C, const float* A, const float* B, int64_t batch, int64
 int mt_gemm_set_precision(int level);
 /* which GEMM engine the last mt_linear_ / mt_matmul_ call used: 1 = tcgen05, 0 = SIMT fp32 */
 int mt_gemm_last_engine(int* engine);
-/* force the engine: -1 auto (default), 0 SIMT only, 1 tcgen05 only (error if the shape
- * is not supported by it).  Test/diagnostic hook.                                       */
+/* force the engine: -1 auto (default), 0 SIMT only, 1 tcgen05 persistent CTA-pair kernel only, 2 tcgen05
+ * mid-size kernel only (error if the shape is not supported by the forced engine).  Test/diagnostic hook. */
 int mt_gemm_set_engine(int engine);
 
 /* ---------------------------------------------------------------- losses ---------- */

@@ -30,6 +30,7 @@ SOURCES = [
     "mt_gemm_simt.cu",
     "mt_gemm_skinny.cu",
     "mt_gemm_tc.cu",
+    "mt_gemm_tc_mid.cu",
     "mt_linear.cu",
     "mt_mlp_small.cu",
     "mt_comm.cu",

@@ -32,6 +32,7 @@ struct Global {
   uint64_t launches = 0;
   int gemm_engine_force = -1;
   int gemm_last_engine = -1;
+  uint64_t gemm_mid_launches = 0;      // launches of the mid-size tcgen05 kernel (mt_gemm_tc_mid_launches)
   void* l2_flush_buf = nullptr;
   size_t l2_flush_bytes = 0;
   bool trace_on = false;               // mt_trace_*: one timed event per launch (a device-side timeline)

@@ -36,5 +36,9 @@ int gemm_skinny_try(const GemmArgs& a);
 // MT_OK if the tcgen05 engine ran it, MT_ERR_UNSUPPORTED if the layout/shape is not one it
 // takes (caller falls back to SIMT), anything else is a real error.
 int gemm_tc_try(const GemmArgs& a);
+// the mid-size tcgen05 kernel (mt_gemm_tc_mid.cu: one 128 x 128 tile x K slice per CTA, slices folded through DSMEM):
+// `wants` = the dispatcher's size window (or engine 2 forced), `try` = run it (MT_ERR_UNSUPPORTED: layout not taken)
+bool gemm_tc_mid_wants(const GemmArgs& a);
+int gemm_tc_mid_try(const GemmArgs& a);
 
 }  // namespace mt

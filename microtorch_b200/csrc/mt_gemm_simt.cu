@@ -276,7 +276,7 @@ MT_API int mt_matmul_f32(float* C, const float* A, const float* B, int64_t batch
     int rc = gemm_tc_try(a);
     if (rc == MT_OK) { g().gemm_last_engine = 1; return MT_OK; }
     if (rc != MT_ERR_UNSUPPORTED) return rc;
-    if (g().gemm_engine_force == 1) return rc;
+    if (g().gemm_engine_force >= 1) return rc;
   }
   g().gemm_last_engine = 0;
   return gemm_simt(a, batch);
@@ -299,7 +299,7 @@ MT_API int mt_gemm_last_engine(int* engine) {
 }
 
 MT_API int mt_gemm_set_engine(int engine) {
-  MT_CHECK_ARG(engine >= -1 && engine <= 1, "mt_gemm_set_engine: engine must be -1, 0 or 1");
+  MT_CHECK_ARG(engine >= -1 && engine <= 2, "mt_gemm_set_engine: engine must be -1, 0, 1 or 2");
   g().gemm_engine_force = engine;
   return MT_OK;
 }

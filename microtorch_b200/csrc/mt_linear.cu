@@ -21,7 +21,7 @@ int run(GemmArgs a, int* engine_min) {
     int rc = gemm_tc_try(a);
     if (rc == MT_OK) return MT_OK;
     if (rc != MT_ERR_UNSUPPORTED) return rc;
-    if (g().gemm_engine_force == 1)
+    if (g().gemm_engine_force >= 1)
       return fail(MT_ERR_UNSUPPORTED, "tcgen05 engine forced but shape M=%lld N=%lld K=%lld is not supported by it",
                   a.M, a.N, a.K);
   }
@@ -89,13 +89,17 @@ MT_API int mt_linear_bwd_f32(float* dX, float* dW, const float* dY, const float*
   auto attempt = [&](GemmArgs a) -> int {
     // first with the fused prologue on tcgen05, then (if refused) SIMT on an explicit dZ
     if (g().gemm_engine_force != 0) {
+      if (Yact && !dZ_tmp && gemm_tc_mid_wants(a)) {   // the mid-size kernel has no prologue flavour: one small dZ pass
+        int rc0 = need_explicit();
+        if (rc0) return rc0;
+      }
       GemmArgs t = a;
       t.A = dZ_tmp ? dZ_tmp : dY;
       t.tanh_src = dZ_tmp ? nullptr : Yact;
       int rc = gemm_tc_try(t);
       if (rc == MT_OK) return MT_OK;
       if (rc != MT_ERR_UNSUPPORTED) return rc;
-      if (g().gemm_engine_force == 1)
+      if (g().gemm_engine_force >= 1)
         return fail(MT_ERR_UNSUPPORTED, "tcgen05 engine forced but backward shape M=%lld N=%lld K=%lld is not supported",
                     a.M, a.N, a.K);
     }

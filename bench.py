@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--precision", default="higher", choices=["high", "higher", "highest"],
                     help="fp32 emulation level of the tensor-core GEMMs (library default: higher)")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the precision=high sub-object")
+    ap.add_argument("--no-mid", action="store_true", help="skip the mid-size-regime sub-object")
     args = ap.parse_args()
     # stdout carries exactly ONE line - the JSON result.  Libraries write banners to fd 1 (NCCL prints its version
     # there when NCCL_DEBUG asks for it), so everything else is sent to stderr for the duration of the run.
@@ -438,6 +439,49 @@ def main():
                         "oracle end to end (tests/test_parity_large_gpu.py), which is why it is not the default"}
         _capi.set_float32_matmul_precision(args.precision)
 
+    # ------------------------------------------------------------- the mid-size regime, for information (N = 1)
+    # A training step whose GEMMs have 2^29 - 2^31 multiply-adds each (MLP 512 -> 1024 -> 1024 -> 512, 2048 rows) through
+    # the same public API: with the dispatcher as shipped (mt_gemm_tc_mid.cu takes them) and with that kernel switched
+    # off (round 1's choice between the SIMT tile and the persistent CTA-pair kernel).
+    mid = None
+    if world == 1 and not args.no_mid:
+        from microtorch_b200.nn.optimizer import SGD
+        np.random.seed(7)
+        mdims, mrows = (512, 1024, 1024, 512), 2048
+        mods = []
+        for a, b in zip(mdims[:-1], mdims[1:]):
+            mods += [nn.Linear(a, b), Tanh()]
+        mmodel = nn.Sequential(*mods[:-1])
+        mx = Tensor(rng.standard_normal((mrows, mdims[0]), dtype=np.float32), device="cuda")
+        mt_ = Tensor(rng.uniform(-1, 1, (mrows, mdims[-1])).astype(np.float32), device="cuda")
+        mloss, mopt = MSELoss(), SGD(mmodel.parameters, lr=0.01)
+        from microtorch_b200.trainer import train_step
+
+        def step_mid():
+            train_step(mmodel, mloss, mopt, mx, mt_, None, None)
+
+        def mid_launches():
+            n = C.c_uint64()
+            lib.mt_gemm_tc_mid_launches(C.byref(n))
+            return n.value
+
+        msteps = 50
+        res = {}
+        for name, on in (("without_mid_kernel", 0), ("with_mid_kernel", 1)):
+            lib.mt_gemm_tc_mid_set(on, 0, 0, 0)
+            for _ in range(5):
+                step_mid()
+            n0 = mid_launches()
+            ms = timed(step_mid, msteps)
+            res[name] = {"ms_per_step": ms / msteps, "samples_per_s": mrows * msteps / (ms / 1e3),
+                         "mid_kernel_launches_per_step": (mid_launches() - n0) / msteps}
+        lib.mt_gemm_tc_mid_set(1, 0, 0, 0)
+        flops = sum(2.0 * mrows * a * b * (3 if i else 2) for i, (a, b) in enumerate(zip(mdims[:-1], mdims[1:])))
+        mid = {"workload": "mlp_512_1024_1024_512_tanh_mse_sgd, 2048 rows (8 GEMMs of 2^30 - 2^31 multiply-adds per step)",
+               "steps": msteps, **res,
+               "speedup": res["without_mid_kernel"]["ms_per_step"] / res["with_mid_kernel"]["ms_per_step"],
+               "step_tflops_logical": flops / (res["with_mid_kernel"]["ms_per_step"] * 1e-3) / 1e12}
+
     # ------------------------------------------------------------- what data parallelism costs, same process (N > 1)
     dp_overhead = None
     if world > 1:
@@ -571,6 +615,8 @@ def main():
         out["c5"] = c5
     if fast is not None:
         out["fast_mode"] = fast
+    if mid is not None:
+        out["mid_regime"] = mid
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     emit(out)

@@ -249,6 +249,23 @@ def main():
         lib.mt_gemm_tc_mid_set(1, 0, 0, 0)
         lib.mt_gemm_tc_mid_set_tile(0, 0)
         lib.mt_gemm_set_precision(1)
+
+    if "ncu" in sys.argv:
+        # a handful of single launches for `ncu --set full -k regex:gemm_mid` (forward, both precisions; dW; dX)
+        rng = np.random.default_rng(3)
+        for (M, N, K) in [(1024, 1024, 1024), (2048, 1024, 1024), (1024, 512, 512)]:
+            X, W, b, dY = (rng.standard_normal((M, K)).astype(np.float32), (rng.standard_normal((N, K)) * 0.05).astype(np.float32),
+                           rng.standard_normal(N).astype(np.float32), rng.standard_normal((M, N)).astype(np.float32))
+            Xd, Wd, bd, dYd = Dev(X), Dev(W), Dev(b), Dev(dY)
+            Y, dX, dW = Dev(shape=(M, N)), Dev(shape=(M, K)), Dev(shape=(N, K))
+            for level in (0, 1):
+                lib.mt_gemm_set_precision(level)
+                for _ in range(2):
+                    _capi.check(lib.mt_linear_fwd_f32(Y.ptr, Xd.ptr, Wd.ptr, bd.ptr, M, N, K, 1))
+            lib.mt_gemm_set_precision(1)
+            for _ in range(2):
+                _capi.check(lib.mt_linear_bwd_f32(dX.ptr, dW.ptr, dYd.ptr, None, Xd.ptr, Wd.ptr, M, N, K, 2))
+            _capi.check(lib.mt_sync())
     return 0
 
 

@@ -28,6 +28,10 @@ COLS = [
     ("smsp__inst_executed.sum", "warp_insts"),
     ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
     ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
+    # the shared-memory port: wavefronts issued by the load/store units (converters, staging, fold) and by the tensor core's
+    # operand reads, each as a share of the port's peak over the whole launch
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_lsu_pct"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_tensor_pct"),
 ]
 
 

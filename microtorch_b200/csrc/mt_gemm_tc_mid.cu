@@ -9,25 +9,30 @@
 // through HBM and a second launch), and the SIMT tile is FMA-bound at ~20 TFLOP/s (profiles/r02_engine_crossover.jsonl).
 //
 // Shape of this kernel:
-//   * one CTA per (128 x 128 output tile, K slice): grid (m-blocks, n-blocks, S), NOT persistent - small tiles and
-//     K slices put every SM to work on a problem of a few hundred tiles' worth of k-blocks;
-//   * the S K-slices of a tile form ONE THREAD-BLOCK CLUSTER (1, 1, S), S in {1, 2, 4, 8}.  Each CTA leaves its fp32
-//     partial tile in its own shared memory; after one cluster barrier CTA s sums rows [128 s / S, 128 (s+1) / S) of
-//     all S partials through distributed shared memory (ld.shared::cluster, slice order 0 .. S-1: deterministic) and
-//     runs the whole epilogue (scale, bias, tanh, tanh', accumulate) on them with coalesced 512-byte row stores.
-//     No partial ever touches HBM and there is no fold launch;
+//   * one CTA per (output tile, K slice): grid (m-blocks, n-blocks, S), NOT persistent - small tiles and K slices put
+//     every SM to work on a problem of a few hundred tiles' worth of k-blocks;
+//   * the S K-slices of a tile form ONE THREAD-BLOCK CLUSTER, S = 1 .. 8 (any number up to the portable cluster size).
+//     Each CTA leaves its fp32 partial tile in its own shared memory; after one cluster barrier CTA s sums rows
+//     [128 s / S, 128 (s+1) / S) of all S partials through distributed shared memory (ld.shared::cluster, slice order
+//     0 .. S-1: deterministic) and all 16 warps run the epilogue (scale, bias, tanh, tanh', accumulate) on them with
+//     coalesced 512-byte row stores.  No partial ever touches HBM and there is no fold launch;
 //   * fourteen converter warps instead of six: with one tile per CTA nobody needs a dedicated epilogue warpgroup
 //     during the K loop, so warps 8-15 convert too and drain a finished TMEM chunk one k-block late (its MMAs have
 //     retired by then, the conversion pipeline never stalls on the tensor core);
-//   * single-CTA MMAs (cta_group::1, M128 N128): no pair handshakes, no cluster barrier in the prologue.
+//   * two tile flavours (template NCTA): 128 x 128 with single-CTA MMAs (cta_group::1: no pair handshakes, no cluster
+//     barrier in the prologue) and 256 x 256 CTA pairs (cta_group::2 inside a cluster of 2 S CTAs) with four times the
+//     flops per k-block for 1.2x the shared-memory traffic; the host picks flavour and S from a measured cost model.
 //
 //   warp 0      TMA producer (one lane)                 full[r]
-//   warp 1      MMA issuer (one lane)                   empty[r], lofree[l], tfull[a]
+//   warp 1      MMA issuer (one lane; pair: leader)     empty[r], lofree[l], tfull[a]
 //   warps 2-7   converters (56 registers)               conv[l]
-//   warps 8-15  converters + chunk drain + cluster fold + epilogue (200 registers)   conv[l], tempty[a]
+//   warps 8-15  converters + chunk drain + staging of the partial tile (200 registers)   conv[l], tempty[a]
+//   all warps   cluster fold + epilogue (128 registers)
 //
-// Roofline: tensor pipe in the K loop (4 TF32 + 4 BF16 MMAs of 64 cycles per k-block of 32), launch / prologue / fold
-// latency around it; DESIGN.md section 4.2 has the measured crossover against both neighbours.
+// Roofline: the K loop is bound by the SHARED-MEMORY PORT, not the tensor pipe - per k-block of 32 a 128 x 128 tile moves
+// 32 KB in by TMA, 32 + 32 KB through the converters and 64 KB of operand reads = 160 KB at 128 B/clk = 1250 cycles for
+// 512 cycles of MMAs (measured 1254) - with launch / prologue / fold latency around it; DESIGN.md section 4.2 has the
+// phase clocks, the ncu counters and the measured crossover against both neighbours.
 #include <algorithm>
 
 #include "mt_common.cuh"

@@ -22,12 +22,17 @@ constexpr int THREADS = 256;
 
 // ------------------------------------------------------------ inner == 1: rows
 // item = (row o, split s); the CTA sums x[o, r0:r1] (* w) and writes one partial.
+// With splits > 1 the partials are folded by the LAST CTA to finish (threadfence + ticket, the loss kernel's idiom):
+// one warp per row sums its `splits` partials lane-strided and then by the shuffle tree - a fixed order - so the
+// second launch of round 1 (10 us of launch latency behind a 45 us pass at 2^26 elements) is gone.
 template <bool HAS_W, bool VEC>
 __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(float* __restrict__ out, const float* __restrict__ x,
                                                               long long outer, long long red, long long splits,
                                                               long long chunk, const float* __restrict__ w,
-                                                              long long so, long long sr) {
+                                                              long long so, long long sr, float* __restrict__ final_out,
+                                                              unsigned int* __restrict__ ticket) {
   __shared__ float smem[THREADS / 32];
+  __shared__ bool is_last;
   const long long items = outer * splits;
   for (long long item = blockIdx.x; item < items; item += gridDim.x) {
     const long long o = item / splits, s = item - o * splits;
@@ -73,6 +78,24 @@ __global__ void __launch_bounds__(THREADS) reduce_rows_kernel(float* __restrict_
     float t = mtd::block_sum<THREADS>((acc0 + acc1) + (acc2 + acc3), smem);
     if (threadIdx.x == 0) out[item] = t;
   }
+  if (ticket) {
+    if (threadIdx.x == 0) {            // thread 0 wrote every partial of this CTA
+      __threadfence();
+      is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const int lane = threadIdx.x & 31;
+      for (long long o = threadIdx.x >> 5; o < outer; o += THREADS / 32) {
+        float acc = 0.f;
+        for (long long k = lane; k < splits; k += 32) acc += __ldcg(out + o * splits + k);
+        acc = mtd::warp_sum(acc);
+        if (lane == 0) final_out[o] = acc;
+      }
+      if (threadIdx.x == 0) *ticket = 0u;   // re-arm for the next launch
+    }
+  }
 }
 
 // short rows: one warp per row
@@ -100,95 +123,126 @@ __global__ void __launch_bounds__(THREADS) reduce_rows_warp_kernel(float* __rest
 // so the stores are conflict-free (the old [TY][TX*V+1] float layout was 4-way conflicted: 7.9 M conflicts per launch).
 constexpr int CT = 256;
 
+// one block's share of one (outer index, split): sums rows [r0, r1) of its TX column-vectors and stores the V sums of
+// every column at `po`.  COHERENT: the rows were written by other CTAs of THIS launch (the fold below): L2 loads (ld.cg)
+// instead of the non-coherent streaming path.
+template <bool HAS_W, int V, bool COHERENT>
+__device__ __forceinline__ void cols_block(float* __restrict__ po, const float* __restrict__ px, const float* __restrict__ pw,
+                                           long long r0, long long r1, long long inner, long long sr, int tx_bits,
+                                           bool col_ok, float* smem) {
+  const int TYr = CT >> tx_bits;
+  const int ty = threadIdx.x >> tx_bits;
+  auto ld4 = [](const float* q) { return COHERENT ? __ldcg(reinterpret_cast<const float4*>(q)) : mtd::ld_stream4(q); };
+  auto ld1 = [](const float* q) { return COHERENT ? __ldcg(q) : *q; };
+  float acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = 0.f;
+  if (col_ok) {
+    long long r = r0 + ty;
+    if (V == 4) {
+      for (; r + 3 * TYr < r1; r += 4 * TYr) {
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a[u] = ld4(px + (r + u * TYr) * inner);
+          if (HAS_W) b[u] = mtd::ld_stream4(pw + (r + u * TYr) * sr);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (HAS_W) {
+            acc[0] += a[u].x * b[u].x; acc[1] += a[u].y * b[u].y; acc[2] += a[u].z * b[u].z; acc[3] += a[u].w * b[u].w;
+          } else {
+            acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
+          }
+        }
+      }
+      for (; r < r1; r += TYr) {
+        float4 a = ld4(px + r * inner);
+        if (HAS_W) {
+          float4 b = mtd::ld_stream4(pw + r * sr);
+          acc[0] += a.x * b.x; acc[1] += a.y * b.y; acc[2] += a.z * b.z; acc[3] += a.w * b.w;
+        } else {
+          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+        }
+      }
+    } else {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent loads in flight
+      for (; r + 3 * TYr < r1; r += 4 * TYr) {
+        if (HAS_W) {
+          a0 += ld1(px + r * inner) * pw[r * sr];
+          a1 += ld1(px + (r + TYr) * inner) * pw[(r + TYr) * sr];
+          a2 += ld1(px + (r + 2 * TYr) * inner) * pw[(r + 2 * TYr) * sr];
+          a3 += ld1(px + (r + 3 * TYr) * inner) * pw[(r + 3 * TYr) * sr];
+        } else {
+          a0 += ld1(px + r * inner);
+          a1 += ld1(px + (r + TYr) * inner);
+          a2 += ld1(px + (r + 2 * TYr) * inner);
+          a3 += ld1(px + (r + 3 * TYr) * inner);
+        }
+      }
+      for (; r < r1; r += TYr) a0 += HAS_W ? ld1(px + r * inner) * pw[r * sr] : ld1(px + r * inner);
+      acc[0] = (a0 + a1) + (a2 + a3);
+    }
+  }
+  if (V == 4) reinterpret_cast<float4*>(smem)[threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  else smem[threadIdx.x] = acc[0];
+  __syncthreads();
+  for (int half = TYr >> 1; half > 0; half >>= 1) {      // fixed tree over the row lanes: deterministic
+    if (ty < half) {
+      if (V == 4) {
+        float4 a = reinterpret_cast<float4*>(smem)[threadIdx.x];
+        const float4 b = reinterpret_cast<float4*>(smem)[threadIdx.x + (half << tx_bits)];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        reinterpret_cast<float4*>(smem)[threadIdx.x] = a;
+      } else {
+        smem[threadIdx.x] += smem[threadIdx.x + (half << tx_bits)];
+      }
+    }
+    __syncthreads();
+  }
+  if (ty == 0 && col_ok) {
+    if (V == 4) *reinterpret_cast<float4*>(po) = reinterpret_cast<float4*>(smem)[threadIdx.x];
+    else po[0] = smem[threadIdx.x];
+  }
+  __syncthreads();
+}
+
+// `tickets` != NULL (splits > 1): `out` holds the partials [outer, splits, inner]; the last of the `splits` CTAs of a
+// (column tile, outer lane) to finish folds that tile's partials - the same block routine over the rows of the partial
+// array - into `final_out`, so a split column reduction is ONE launch.
 template <bool HAS_W, int V>
 __global__ void __launch_bounds__(CT) reduce_cols_kernel(float* __restrict__ out, const float* __restrict__ x,
                                                          long long outer, long long red, long long inner,
                                                          long long splits, long long chunk,
                                                          const float* __restrict__ w, long long so, long long sr,
-                                                         long long si, int tx_bits) {
+                                                         long long si, int tx_bits, float* __restrict__ final_out,
+                                                         unsigned int* __restrict__ tickets) {
   __shared__ __align__(16) float smem[CT * V];
-  const int TXr = 1 << tx_bits, TYr = CT >> tx_bits;
-  const int tx = threadIdx.x & (TXr - 1), ty = threadIdx.x >> tx_bits;
+  __shared__ bool is_last;
+  const int TXr = 1 << tx_bits;
+  const int tx = threadIdx.x & (TXr - 1);
   const long long col = ((long long)blockIdx.x * TXr + tx) * V;
+  const bool col_ok = col < inner;
   const long long s = blockIdx.y;
   const long long r0 = s * chunk;
   long long r1 = r0 + chunk;
   if (r1 > red) r1 = red;
-  for (long long o = blockIdx.z; o < outer; o += gridDim.z) {
-    float acc[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = 0.f;
-    if (col < inner) {
-      const float* px = x + (o * red) * inner + col;
-      const float* pw = HAS_W ? w + o * so + col * si : nullptr;
-      long long r = r0 + ty;
-      if (V == 4) {
-        for (; r + 3 * TYr < r1; r += 4 * TYr) {
-          float4 a[4], b[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            a[u] = mtd::ld_stream4(px + (r + u * TYr) * inner);
-            if (HAS_W) b[u] = mtd::ld_stream4(pw + (r + u * TYr) * sr);
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (HAS_W) {
-              acc[0] += a[u].x * b[u].x; acc[1] += a[u].y * b[u].y; acc[2] += a[u].z * b[u].z; acc[3] += a[u].w * b[u].w;
-            } else {
-              acc[0] += a[u].x; acc[1] += a[u].y; acc[2] += a[u].z; acc[3] += a[u].w;
-            }
-          }
-        }
-        for (; r < r1; r += TYr) {
-          float4 a = mtd::ld_stream4(px + r * inner);
-          if (HAS_W) {
-            float4 b = mtd::ld_stream4(pw + r * sr);
-            acc[0] += a.x * b.x; acc[1] += a.y * b.y; acc[2] += a.z * b.z; acc[3] += a.w * b.w;
-          } else {
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-          }
-        }
-      } else {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent loads in flight
-        for (; r + 3 * TYr < r1; r += 4 * TYr) {
-          if (HAS_W) {
-            a0 += px[r * inner] * pw[r * sr];
-            a1 += px[(r + TYr) * inner] * pw[(r + TYr) * sr];
-            a2 += px[(r + 2 * TYr) * inner] * pw[(r + 2 * TYr) * sr];
-            a3 += px[(r + 3 * TYr) * inner] * pw[(r + 3 * TYr) * sr];
-          } else {
-            a0 += px[r * inner];
-            a1 += px[(r + TYr) * inner];
-            a2 += px[(r + 2 * TYr) * inner];
-            a3 += px[(r + 3 * TYr) * inner];
-          }
-        }
-        for (; r < r1; r += TYr) a0 += HAS_W ? px[r * inner] * pw[r * sr] : px[r * inner];
-        acc[0] = (a0 + a1) + (a2 + a3);
-      }
-    }
-    if (V == 4) reinterpret_cast<float4*>(smem)[threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    else smem[threadIdx.x] = acc[0];
+  for (long long o = blockIdx.z; o < outer; o += gridDim.z)
+    cols_block<HAS_W, V, false>(out + (o * splits + s) * inner + col, x + (o * red) * inner + col,
+                                HAS_W ? w + o * so + col * si : nullptr, r0, r1, inner, sr, tx_bits, col_ok, smem);
+  if (tickets) {
+    unsigned int* ticket = tickets + (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+    __threadfence();                   // this CTA's partials (written by its ty == 0 threads) before the ticket
     __syncthreads();
-    for (int half = TYr >> 1; half > 0; half >>= 1) {      // fixed tree over the row lanes: deterministic
-      if (ty < half) {
-        if (V == 4) {
-          float4 a = reinterpret_cast<float4*>(smem)[threadIdx.x];
-          const float4 b = reinterpret_cast<float4*>(smem)[threadIdx.x + (half << tx_bits)];
-          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          reinterpret_cast<float4*>(smem)[threadIdx.x] = a;
-        } else {
-          smem[threadIdx.x] += smem[threadIdx.x + (half << tx_bits)];
-        }
-      }
-      __syncthreads();
-    }
-    if (ty == 0 && col < inner) {
-      float* po = out + (o * splits + s) * inner + col;
-      if (V == 4) *reinterpret_cast<float4*>(po) = reinterpret_cast<float4*>(smem)[threadIdx.x];
-      else po[0] = smem[threadIdx.x];
-    }
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.y - 1);
     __syncthreads();
+    if (is_last) {
+      __threadfence();
+      for (long long o = blockIdx.z; o < outer; o += gridDim.z)
+        cols_block<false, V, true>(final_out + o * inner + col, out + (o * splits) * inner + col, nullptr, 0, splits, inner,
+                                   0, tx_bits, col_ok, smem);
+      if (threadIdx.x == 0) *ticket = 0u;   // re-arm for the next launch
+    }
   }
 }
 
@@ -240,6 +294,17 @@ __global__ void __launch_bounds__(CT) reduce_cols_flat_kernel(float* __restrict_
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// tickets of the single-launch split reductions: zero when idle (the last CTA re-arms its own), one stream -> no sharing
+constexpr long long TICKETS = 4096;
+unsigned int* g_tickets = nullptr;
+int g_single_launch = 1;               // 0: round 1's two-launch form (mt_reduce_set_single_launch, A/B measurements)
+int ensure_tickets() {
+  if (g_tickets) return MT_OK;
+  MT_CUDA(cudaMalloc((void**)&g_tickets, sizeof(unsigned int) * TICKETS));
+  MT_CUDA(cudaMemset(g_tickets, 0, sizeof(unsigned int) * TICKETS));
+  return MT_OK;
+}
+
 int reduce_rows(float* out, const float* x, long long outer, long long red, const float* w, long long so, long long sr) {
   cudaStream_t st = g().stream;
   const int sms = g().sm_count;
@@ -269,12 +334,19 @@ int reduce_rows(float* out, const float* x, long long outer, long long red, cons
     dst = partial;
   }
   const int grid = (int)std::min<long long>(outer * splits, (long long)sms * 8);
-#define MT_ROWS(HW, VC) reduce_rows_kernel<HW, VC><<<grid, THREADS, 0, st>>>(dst, x, outer, red, splits, chunk, w, so, sr)
+  unsigned int* ticket = nullptr;
+  if (splits > 1 && g_single_launch) {
+    int rc = ensure_tickets();
+    if (rc) return rc;
+    ticket = g_tickets;
+  }
+#define MT_ROWS(HW, VC) \
+  reduce_rows_kernel<HW, VC><<<grid, THREADS, 0, st>>>(dst, x, outer, red, splits, chunk, w, so, sr, out, ticket)
   if (w) { if (vec) MT_ROWS(true, true); else MT_ROWS(true, false); }
   else { if (vec) MT_ROWS(false, true); else MT_ROWS(false, false); }
 #undef MT_ROWS
   MT_LAUNCHED();
-  if (splits > 1) {
+  if (splits > 1 && !ticket) {
     int rc = reduce_rows(out, partial, outer, splits, nullptr, 0, 0);
     return rc;
   }
@@ -322,13 +394,20 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
     dst = partial;
   }
   dim3 grid((unsigned)tiles, (unsigned)splits, (unsigned)oz);
-#define MT_COLS(HW, VV) \
-  reduce_cols_kernel<HW, VV><<<grid, CT, 0, st>>>(dst, x, outer, red, inner, splits, chunk, w, so, sr, si, tx_bits)
+  unsigned int* tickets = nullptr;
+  if (splits > 1 && g_single_launch && tiles * oz <= TICKETS - 1) {
+    int rc = ensure_tickets();
+    if (rc) return rc;
+    tickets = g_tickets + 1;          // slot 0 belongs to reduce_rows
+  }
+#define MT_COLS(HW, VV)                                                                                                  \
+  reduce_cols_kernel<HW, VV><<<grid, CT, 0, st>>>(dst, x, outer, red, inner, splits, chunk, w, so, sr, si, tx_bits, out, \
+                                                  tickets)
   if (w) { if (vec) MT_COLS(true, 4); else MT_COLS(true, 1); }
   else { if (vec) MT_COLS(false, 4); else MT_COLS(false, 1); }
 #undef MT_COLS
   MT_LAUNCHED();
-  if (splits > 1) {
+  if (splits > 1 && !tickets) {
     // the fold of the partials is ONE more launch (it used to split again: three launches for a 2^26-element
     // sum(axis=0), 10 us of launch latency on a 43 us kernel)
     int rc = reduce_cols(out, partial, outer, splits, inner, nullptr, 0, 0, 0, false);
@@ -446,6 +525,13 @@ int reduce_extreme(float* out, const float* x, long long outer, long long red, l
 }
 
 }  // namespace
+
+// diagnostic knob: 0 = split reductions as two launches (main pass + fold, round 1), 1 (default) = one launch whose last
+// CTA folds the partials
+extern "C" __attribute__((visibility("default"))) int mt_reduce_set_single_launch(int v) {
+  g_single_launch = v ? 1 : 0;
+  return MT_OK;
+}
 
 MT_API int mt_reduce_extreme_f32(int is_max, float* out, const float* x, int64_t outer, int64_t red, int64_t inner) {
   MT_REQUIRE_INIT();

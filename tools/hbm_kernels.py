@@ -27,11 +27,14 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--once", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--two-launch", action="store_true", help="split reductions as main pass + fold launch (round 1's form)")
     args = ap.parse_args()
     from bench import ClockSampler, load_peaks
     from microtorch_b200 import _capi
     _capi.require_device(0)
     lib = _capi.lib()
+    if args.two_launch:
+        lib.mt_reduce_set_single_launch(0)
     from microtorch_b200.cuda import kernels as K
     from microtorch_b200.cuda.array import DeviceArray
     peak = load_peaks()["hbm_gbs"]

@@ -476,6 +476,14 @@ def main():
             res[name] = {"ms_per_step": ms / msteps, "samples_per_s": mrows * msteps / (ms / 1e3),
                          "mid_kernel_launches_per_step": (mid_launches() - n0) / msteps}
         lib.mt_gemm_tc_mid_set(1, 0, 0, 0)
+        # the same step as ONE CUDA graph (graph.GraphedStep): what remains when the platform's per-launch cost is gone
+        from microtorch_b200.graph import GraphedStep
+        gstep = GraphedStep(step_mid, warmup=2)
+        for _ in range(5):
+            gstep.replay()
+        ms = timed(gstep.replay, msteps)
+        gstep.close()
+        res["with_mid_kernel_graphed"] = {"ms_per_step": ms / msteps, "samples_per_s": mrows * msteps / (ms / 1e3)}
         flops = sum(2.0 * mrows * a * b * (3 if i else 2) for i, (a, b) in enumerate(zip(mdims[:-1], mdims[1:])))
         mid = {"workload": "mlp_512_1024_1024_512_tanh_mse_sgd, 2048 rows (8 GEMMs of 2^30 - 2^31 multiply-adds per step)",
                "steps": msteps, **res,

@@ -167,3 +167,53 @@ def test_short_and_empty_slices_do_not_deadlock(lib, tile, splits):
             _capi.check(lib.mt_linear_fwd_f32(Y.ptr, Xd.ptr, Wd.ptr, bd.ptr, M, N, K, 1))
         _capi.check(lib.mt_sync())
     assert gemm_err(Y.get(), np.tanh(X.astype(np.float64) @ W.astype(np.float64).T + b)) < GEMM_TOL
+
+
+# ----------------------------------------------------------------------------- through the public API
+def test_mid_size_training_steps_vs_oracle_and_graph_replay():
+    """A training step whose GEMMs all fall into the mid-size window (MLP 256 -> 384 -> 512 -> 128 with Tanh, 2048 rows:
+    2^26 - 2^28.6 multiply-adds each) through the unchanged MicroTorch API (demo.ipynb:5178-5189): loss, every weight
+    gradient and post-SGD weight of 3 steps against the oracle (the NumPy restatement of the reference's step), 1e-4
+    norm-wise; then the same step captured as ONE CUDA graph (cluster launches inside stream capture) replays the eager
+    loss stream bit for bit."""
+    import microtorch_b200.nn as nn
+    from microtorch_b200 import workloads as W
+    from microtorch_b200.graph import GraphedStep
+    from microtorch_b200.nn.activation import Tanh
+    from microtorch_b200.nn.loss import MSELoss
+    from microtorch_b200.nn.optimizer import SGD
+    from microtorch_b200.tensor import Tensor
+    from microtorch_b200.trainer import train_step
+    from oracle import workloads as OW
+
+    lib = _capi.lib()
+    wl = W.Workload("mid_mlp", (256, 384, 512, 128), "mse", 0.05, 2048, seed=11)
+    ref = OW.run_steps(wl, 3)
+
+    def fresh():
+        model, x, t = W.setup(wl, nn.Linear, Tanh, nn.Sequential)
+        return model, Tensor(x, device="cuda"), Tensor(t, device="cuda"), MSELoss(), SGD(model.parameters, lr=wl.lr)
+
+    model, X, T, loss_fn, opt = fresh()
+    n0 = mid_launches(lib)
+    losses = [float(train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim).item()) for _ in range(3)]
+    assert mid_launches(lib) - n0 == 3 * 8, "3 forward + 3 dW + 2 dX products per step belong to the mid-size kernel"
+    np.testing.assert_allclose(np.array(losses, np.float32), ref["losses"], rtol=1e-4)
+    params = list(model.parameters())
+    for i, p in enumerate(params):
+        got, want = p.data.get().astype(np.float64), ref["params"][i].astype(np.float64)
+        assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+        gg, gw = p.grad.get().astype(np.float64), ref["grads"][i].astype(np.float64)
+        assert np.abs(gg - gw).max() <= 1e-4 * max(np.abs(gw).max(), 1e-30)
+
+    # eager stream of 6 steps vs 2 eager warm-up steps + 4 graph replays
+    model, X, T, loss_fn, opt = fresh()
+    eager = [train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim).item() for _ in range(6)]
+    model, X, T, loss_fn, opt = fresh()
+    step = GraphedStep(lambda: train_step(model, loss_fn, opt, X, T, wl.pred_map, wl.squeeze_dim), warmup=2)
+    replayed = []
+    for _ in range(4):
+        step.replay()
+        replayed.append(step.result.item())
+    step.close()
+    assert replayed == eager[2:6]

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Where should Linear GEMMs switch from the SIMT fp32 tile to the tcgen05 split-fp32 kernel?  Times mt_linear_fwd_f32 on both
+"""Where should Linear GEMMs switch between the SIMT fp32 tile, the mid-size tcgen05 kernel and the persistent tcgen05 kernel?  Times mt_linear_fwd_f32 on both
 engines over a grid of (M, N, K) and prints one JSON line per shape (run under gpurun).  The dispatch threshold in
 mt_gemm_tc.cu (gemm_tc_try) comes from this table."""
 import ctypes as C
@@ -44,7 +44,7 @@ def main():
         b = DeviceArray.from_host(rng.standard_normal(N).astype(np.float32))
         Y = DeviceArray.empty((M, N))
         rec = {"M": M, "N": N, "K": K, "mmacs": M * N * K / 1e6}
-        for name, eng in (("simt", 0), ("tcgen05", 1)):
+        for name, eng in (("simt", 0), ("tcgen05", 1), ("tcgen05_mid", 2)):
             lib.mt_gemm_set_engine(eng)
             try:
                 fn = lambda: _capi.check(lib.mt_linear_fwd_f32(Y.ptr, X.ptr, Wt.ptr, b.ptr, M, N, K, 1))
@@ -55,6 +55,8 @@ def main():
                 lib.mt_gemm_set_engine(-1)
         if rec["simt_us"] and rec["tcgen05_us"]:
             rec["tc_speedup"] = round(rec["simt_us"] / rec["tcgen05_us"], 2)
+        if rec["simt_us"] and rec.get("tcgen05_mid_us"):
+            rec["mid_speedup"] = round(min(rec["simt_us"], rec["tcgen05_us"] or 1e30) / rec["tcgen05_mid_us"], 2)
         print(json.dumps(rec), flush=True)
 
 

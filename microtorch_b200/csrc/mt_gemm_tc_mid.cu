@@ -639,6 +639,12 @@ static int launch_plan(const GemmArgs& a, long long lda, long long ldb, int S, i
   cfg.numAttrs = 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ma, mb, p);
   prof_end(token);
+  if (le == cudaErrorLaunchOutOfResources || le == cudaErrorInvalidConfiguration || le == cudaErrorInvalidClusterSize) {
+    // a device (or partition) that cannot host this cluster shape: leave the problem to the other GPU engines instead of
+    // failing the call - unless this kernel was asked for by name (engine 2)
+    cudaGetLastError();
+    if (g().gemm_engine_force != 2) return MT_ERR_UNSUPPORTED;
+  }
   if (le != cudaSuccess) return fail(MT_ERR_CUDA, "gemm_mid launch failed: %s", cudaGetErrorString(le));
   g().launches++;
   g().gemm_mid_launches++;

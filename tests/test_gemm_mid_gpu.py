@@ -217,3 +217,10 @@ def test_mid_size_training_steps_vs_oracle_and_graph_replay():
         replayed.append(step.result.item())
     step.close()
     assert replayed == eager[2:6]
+
+
+@pytest.mark.parametrize("tile,splits", [(0, 0), (1, 8), (1, 1), (2, 4)])
+def test_mid_kernel_long_k(lib, tile, splits):
+    """K = 16 384 on a 256 x 256 output (the dW of a narrow layer over a long batch: overload.py:153 with K = rows): up to 512
+    k-blocks per CTA, i.e. dozens of TMEM chunks through both accumulator buffers and every ring wrap-around"""
+    check_layer(lib, 256, 256, 16384, tile, splits, 1)

@@ -358,6 +358,20 @@ gemm_splitfp32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int kb_begin = work_kb0(w), kb_end = work_kb1(w);
       for (int kb0 = kb_begin; kb0 < kb_end; kb0 += chunk_kb, ++cc) {
         const int acc = cc & 1;
+        if (kb0 + chunk_kb >= kb_end && (p.epi_tanh || p.accumulate)) {
+          // last chunk of the tile: its MMAs take a few microseconds - pull this thread's row of the epilogue's DRAM
+          // operand (the tanh' source, or the old C) into L2 now, so that the epilogue's loads are L2 hits
+          const long long prow = m0 + quad * 32 + lane;
+          if (prow < p.M) {
+            const float* src = p.epi_tanh ? p.epi_tanh + prow * p.N
+                                          : p.C + (long long)work_split(w) * p.M * p.N + prow * p.N;
+#pragma unroll
+            for (int c = 0; c < COLS; c += 32) {
+              const long long n = n0 + half * COLS + c;
+              if (n < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + n));
+            }
+          }
+        }
         mbar_wait(tfull_bar(acc), (cc >> 1) & 1, 4);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + acc * BN + half * COLS;
@@ -381,34 +395,59 @@ gemm_splitfp32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           else mbar_arrive(tempty_bar(acc));
         }
       }
-      // ---- tile epilogue: (mix-mode scale), bias, tanh, (accumulate), store.  One row per thread, 128 B per 32 columns.
+      // ---- tile epilogue: (mix-mode scale), bias, tanh, tanh' of the producer, (accumulate), store.  One row per thread,
+      // 128 B per 32 columns.  The global operand of the epilogue - the tanh' source (dX), the old C (accumulate) or the bias
+      // (forward) - is loaded EB vectors at a time BEFORE any arithmetic or store of the batch: written as one loop the
+      // compiler had to keep load -> math -> store order per vector (the stores may alias the next load), i.e. 32
+      // serialised global-memory round trips per tile - ~38 us for the dX epilogue, during which these warps do not
+      // drain TMEM chunks and the MMA warp stalls after two chunks (ncu: tensor pipe 73 % active in dX against 81 % in dW).
       const bool mix_scale = p.mix || !p.write_hi;   // centred split (every mode but write_hi): accumulator scaled by S
       const long long row = m0 + quad * 32 + lane;
       if (row < p.M) {
         float* crow = p.C + (long long)work_split(w) * p.M * p.N + row * p.N;   // split partials are stacked
+        const float* erow = p.epi_tanh ? p.epi_tanh + row * p.N : nullptr;
         const long long nb0 = n0 + half * COLS;
+        constexpr int EB = 4;                                        // vectors per batch
+        const int emode = p.epi_tanh ? 1 : (p.accumulate ? 2 : (p.bias ? 3 : 0));   // which operand is batched
 #pragma unroll
-        for (int j = 0; j < COLS; j += 4) {
-          const long long n = nb0 + j;
-          if (n < p.N) {                       // N % 4 == 0 (checked on the host)
-            float4 v = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
-            if (mix_scale) { v.x *= kMixScale; v.y *= kMixScale; v.z *= kMixScale; v.w *= kMixScale; }
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        for (int j0 = 0; j0 < COLS; j0 += 4 * EB) {
+          float4 aux[EB];
+#pragma unroll
+          for (int u = 0; u < EB; ++u) {
+            const long long n = nb0 + j0 + 4 * u;
+            if (n < p.N) {                     // N % 4 == 0 (checked on the host)
+              if (emode == 1) aux[u] = __ldg(reinterpret_cast<const float4*>(erow + n));
+              else if (emode == 2) aux[u] = *reinterpret_cast<const float4*>(crow + n);
+              else if (emode == 3) aux[u] = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             }
-            if (p.act == MT_ACT_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
-            if (p.epi_tanh) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(p.epi_tanh + row * p.N + n));
-              v.x = __fmul_rn(v.x, __fsub_rn(1.f, __fmul_rn(t.x, t.x)));
-              v.y = __fmul_rn(v.y, __fsub_rn(1.f, __fmul_rn(t.y, t.y)));
-              v.z = __fmul_rn(v.z, __fsub_rn(1.f, __fmul_rn(t.z, t.z)));
-              v.w = __fmul_rn(v.w, __fsub_rn(1.f, __fmul_rn(t.w, t.w)));
+          }
+#pragma unroll
+          for (int u = 0; u < EB; ++u) {
+            const int j = j0 + 4 * u;
+            const long long n = nb0 + j;
+            if (n < p.N) {
+              float4 v = make_float4(run[j], run[j + 1], run[j + 2], run[j + 3]);
+              if (mix_scale) { v.x *= kMixScale; v.y *= kMixScale; v.z *= kMixScale; v.w *= kMixScale; }
+              if (p.bias) {
+                const float4 b = emode == 3 ? aux[u] : __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (p.act == MT_ACT_TANH) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+              if (emode == 1) {
+                const float4 t = aux[u];
+                v.x = __fmul_rn(v.x, __fsub_rn(1.f, __fmul_rn(t.x, t.x)));
+                v.y = __fmul_rn(v.y, __fsub_rn(1.f, __fmul_rn(t.y, t.y)));
+                v.z = __fmul_rn(v.z, __fsub_rn(1.f, __fmul_rn(t.z, t.z)));
+                v.w = __fmul_rn(v.w, __fsub_rn(1.f, __fmul_rn(t.w, t.w)));
+              }
+              float4* dst = reinterpret_cast<float4*>(crow + n);
+              if (p.accumulate) {
+                const float4 o = emode == 2 ? aux[u] : *dst;
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              if (p.store_cs) __stcs(dst, v);
+              else *dst = v;
             }
-            float4* dst = reinterpret_cast<float4*>(crow + n);
-            if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            if (p.store_cs) __stcs(dst, v);
-            else *dst = v;
           }
         }
       }

@@ -72,7 +72,9 @@ int mt_graph_begin(void);
 int mt_graph_end(void** graph_handle);
 int mt_graph_launch(void* graph_handle);
 int mt_graph_destroy(void* graph_handle);
-/* overwrite a buffer larger than L2 (timing hygiene between timed iterations)           */
+/* timing hygiene between timed iterations: overwrite a buffer larger than L2, then read
+ * another one, so that L2 is cold AND holds no dirty lines whose write-back the timed
+ * kernel would pay for                                                                  */
 int mt_l2_flush(void);
 /* per-kernel timing of the dominant kernel (bench roofline): when enabled, every tcgen05
  * GEMM launch is bracketed by CUDA events on the compute stream; mt_prof_gemm synchronises

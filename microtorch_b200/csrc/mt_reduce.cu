@@ -372,9 +372,15 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
   }
   int tx_bits = 0;
   while (tx_bits < 6 && (1LL << tx_bits) < vcols) ++tx_bits;    // TX = min(64, pow2 >= column-vectors)
+  const long long oz = std::min<long long>(outer, 65535);
+  // few column tiles and many rows (tall-thin: (131072, 512) is 2 tiles of 64 vectors): the reduced axis is split ~300
+  // ways and ONE CTA per tile folds the partials with only 4 row lanes - ~19 serial L2 round trips while the machine
+  // idles.  Narrower tiles (down to 16 vectors = 256 contiguous bytes per row, still whole lines) give more tiles, fewer
+  // splits per tile and 4x the row lanes: the fold shrinks to 2 round trips.
+  if (may_split && vec)
+    while (tx_bits > 4 && ceil_div(vcols, 1LL << tx_bits) * oz * 16 <= sms && red >= 4096) --tx_bits;
   const int TXr = 1 << tx_bits, TYr = CT >> tx_bits;
   const long long tiles = ceil_div(vcols, (long long)TXr);
-  const long long oz = std::min<long long>(outer, 65535);
   long long splits = 1;
   if (may_split && tiles * oz < 4LL * sms) {
     // fill the machine (4 CTAs per SM) but leave every row lane at least ~8 rows of work

@@ -637,14 +637,35 @@ MT_API int mt_fill_f32(float* out, size_t n, float value) {
   return MT_OK;
 }
 
+// Reads `n4` vectors and keeps the compiler from dropping the loads (the store never happens: the buffer is zero).
+__global__ void __launch_bounds__(256) l2_sweep_kernel(const float4* __restrict__ buf, size_t n4, float* sink) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldcg(buf + i);
+    acc += (v.x + v.y) + (v.z + v.w);
+  }
+  if (acc == 12345.678f) *sink = acc;
+}
+
+// Timing hygiene between timed iterations: overwrite 256 MiB (> the 126 MB L2), then READ another 256 MiB.  The write
+// alone evicts the previous iteration's data but leaves up to an L2-full of DIRTY lines behind, and the kernel being
+// timed then pays for their write-back (~100 MB of DRAM writes = ~15 us charged to a 268 MB read pass: the event-timed
+// reductions of round 1 / early round 2 read 12 us slower than the same launches under ncu, whose own cache control
+// invalidates).  After the read sweep L2 is cold AND clean.
 MT_API int mt_l2_flush(void) {
   MT_REQUIRE_INIT();
   Global& G = g();
+  const size_t half = (size_t)256 << 20;   // 256 MiB > 126 MB L2
   if (!G.l2_flush_buf) {
-    G.l2_flush_bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+    G.l2_flush_bytes = 2 * half;
     MT_CUDA(cudaMalloc(&G.l2_flush_buf, G.l2_flush_bytes));
+    MT_CUDA(cudaMemsetAsync(G.l2_flush_buf, 0, G.l2_flush_bytes, G.stream));
   }
-  MT_CUDA(cudaMemsetAsync(G.l2_flush_buf, 0, G.l2_flush_bytes, G.stream));
+  MT_CUDA(cudaMemsetAsync(G.l2_flush_buf, 0, half, G.stream));
+  float* base = static_cast<float*>(G.l2_flush_buf);
+  l2_sweep_kernel<<<G.sm_count * 8, 256, 0, G.stream>>>(reinterpret_cast<const float4*>(base + half / 4), half / 16, base);
+  MT_CUDA(cudaGetLastError());
   return MT_OK;
 }
 

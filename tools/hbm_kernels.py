@@ -2,7 +2,7 @@
 """The HBM-bound kernels of the training step, one by one, at 2^26 and 2^28 elements (run under gpurun).
 
 For VERDICT r1 item 3: achieved GB/s (ALGORITHMIC bytes of SURVEY.md 8(d) / CUDA-event time, L2 flushed between
-launches) of bin_flat / bin_2d / unary / reduce_rows / reduce_cols / loss_kernel / sgd_multi_kernel / zero_multi and
+launches - mt_l2_flush leaves it cold and clean) of bin_flat / bin_2d / unary / reduce_rows / reduce_cols / loss_kernel / sgd_multi_kernel / zero_multi and
 the skinny head GEMMs, each row with the nvidia-smi clocks and throttle reasons sampled while it ran.
 
     python tools/hbm_kernels.py                # JSON lines (timings + clocks)
@@ -94,7 +94,7 @@ def main():
             "sgd_multi_kernel": (lambda: K.sgd_multi([x], [y], 1e-9), 3 * B),
             "zero_multi_kernel": (lambda: K.zero_multi([out]), B),
         }
-        if p <= 26:
+        if True:
             # tall-thin un-broadcast shapes (reduce_cols at 17-54 % with bank conflicts)
             for rr, cc in ((n // 8, 8), (n // 32, 32), (n // 512, 512), (2, n // 2)):
                 tt = x.reshape((rr, cc))

@@ -2,7 +2,7 @@
 
 A program is data - leaf arrays, a list of (op, input nodes, arguments) and weighted terminal nodes - generated from a
 seed with a NumPy float32 shadow evaluation that keeps every intermediate finite, away from the singularities of
-log / sqrt / division / fractional powers and free of ties under max.  `run_program` executes a program with ANY Tensor
+log / sqrt / division / fractional powers and free of (near-)ties under max / maximum / minimum.  `run_program` executes a program with ANY Tensor
 class that has the reference's surface (src/tensor/tensor.py): the live reference (build container), this package's
 NumPy path, or this package's CUDA path.  The loss is sum_k (node_k * w_k).sum(); `run_program` returns the terminal
 values, the loss and every leaf gradient as host arrays.
@@ -128,9 +128,9 @@ _WEIGHTS /= _WEIGHTS.sum()
 _BINARY = ("add", "sub", "mul", "div", "maximum", "minimum")
 
 
-def _rand_shape(rng) -> Tuple[int, ...]:
+def _rand_shape(rng, dims) -> Tuple[int, ...]:
     rank = int(rng.choice([1, 2, 2, 2, 3, 3, 4]))
-    return tuple(int(rng.choice(DIMS)) for _ in range(rank))
+    return tuple(int(rng.choice(dims)) for _ in range(rank))
 
 
 def _variant_shape(rng, base: Tuple[int, ...]) -> Tuple[int, ...]:
@@ -148,7 +148,7 @@ def _variant_shape(rng, base: Tuple[int, ...]) -> Tuple[int, ...]:
     return tuple(s)
 
 
-def _pick_args(rng, op: str, a: np.ndarray, vals: List[np.ndarray]):
+def _pick_args(rng, op: str, a: np.ndarray, vals: List[np.ndarray], max_elems: int = MAX_ELEMS):
     """Returns (input indices beyond the first, args) or None when `op` does not apply to `a`."""
     nd = a.ndim
     if op in _BINARY:
@@ -158,7 +158,7 @@ def _pick_args(rng, op: str, a: np.ndarray, vals: List[np.ndarray]):
                 shp = np.broadcast_shapes(a.shape, b.shape)
             except ValueError:
                 continue
-            if int(np.prod(shp)) <= MAX_ELEMS:
+            if int(np.prod(shp)) <= max_elems:
                 cands.append(j)
         if not cands:
             return None
@@ -171,8 +171,8 @@ def _pick_args(rng, op: str, a: np.ndarray, vals: List[np.ndarray]):
             return None                       # x - x, x / x: the gradient is pure cancellation noise
         if op == "div" and np.abs(vals[j]).min(initial=1.0) < 0.1:
             return None
-        if op in ("maximum", "minimum") and np.any(np.broadcast_arrays(a, vals[j])[0] == np.broadcast_arrays(a, vals[j])[1]):
-            return None                       # a tie: the sub-gradient split is a convention, not arithmetic
+        if op in ("maximum", "minimum") and np.abs(a - vals[j]).min(initial=1.0) <= 1e-4 * (1.0 + np.abs(a).max(initial=0.0)):
+            return None                       # a (near-)tie: which side wins is decided by the last ulp of the operands
         return (j,), {}
     if op in ("sadd", "sradd", "ssub", "srsub", "smul", "srmul", "sdiv", "srdiv"):
         if op == "srdiv" and np.abs(a).min(initial=1.0) < 0.1:
@@ -211,6 +211,9 @@ def _pick_args(rng, op: str, a: np.ndarray, vals: List[np.ndarray]):
         m = a.max(axis=axis, keepdims=True)
         if np.any((a == m).sum(axis=axis, keepdims=True) != 1):
             return None
+        runner_up = np.where(a == m, -np.inf, a).max(axis=axis, keepdims=True)
+        if np.any(m - runner_up <= 1e-4 * (1.0 + np.abs(m))):
+            return None                       # the winner must not depend on the last ulp of the producer (tanh, exp ...)
         return (), {"axis": axis, "keepdims": keep}
     if op == "transpose":
         if nd < 2 or rng.random() < 0.3:
@@ -248,7 +251,7 @@ def _pick_args(rng, op: str, a: np.ndarray, vals: List[np.ndarray]):
         shape = [int(rng.choice([2, 3, 5])) if (d == 1 and rng.random() < 0.7) else d for d in a.shape]
         if rng.random() < 0.5 and nd < 4:
             shape = [int(rng.choice([2, 3]))] + shape
-        if tuple(shape) == a.shape or int(np.prod(shape)) > MAX_ELEMS:
+        if tuple(shape) == a.shape or int(np.prod(shape)) > max_elems:
             return None
         return (), {"shape": tuple(shape)}
     if op == "getitem":
@@ -285,13 +288,23 @@ def _pick_args(rng, op: str, a: np.ndarray, vals: List[np.ndarray]):
     raise KeyError(op)
 
 
-def make_program(seed: int, n_ops: int = 12) -> Program:
+LARGE_DIMS = [1, 2, 7, 64, 100, 257, 512, 1024]
+LARGE_MAX_ELEMS = 1 << 22
+LARGE = dict(dims=LARGE_DIMS, max_elems=LARGE_MAX_ELEMS, min_base=1 << 16)
+
+
+def make_program(seed: int, n_ops: int = 12, dims=DIMS, max_elems: int = MAX_ELEMS, min_base: int = 0) -> Program:
+    """`**LARGE` gives the programs of the large variant: odd extents next to powers
+    of two, up to 4 M elements per node - the vectorised / grid-stride / split-reduction paths and, through matmul, the
+    tensor-core engines."""
     rng = np.random.default_rng(seed)
     prog = Program(seed)
-    base = _rand_shape(rng)
+    base = _rand_shape(rng, dims)
+    while int(np.prod(base)) > max_elems or int(np.prod(base)) < min_base:
+        base = _rand_shape(rng, dims)
     shapes = [base] + [_variant_shape(rng, base) for _ in range(int(rng.integers(1, 4)))]
     if rng.random() < 0.6:                                        # a partner for matmul
-        shapes.append((base[-1], int(rng.choice(DIMS))))
+        shapes.append((base[-1], int(rng.choice(dims))))
     vals: List[np.ndarray] = []
     for shp in shapes:
         lo, hi = (-1.5, 1.5) if rng.random() < 0.25 else (0.5, 1.5)
@@ -304,7 +317,7 @@ def make_program(seed: int, n_ops: int = 12) -> Program:
             op = _NAMES[int(rng.choice(len(_NAMES), p=_WEIGHTS))]
             recent = rng.random() < 0.6
             i = int(rng.integers(max(0, len(vals) - 3), len(vals))) if recent else int(rng.integers(0, len(vals)))
-            picked = _pick_args(rng, op, vals[i], vals)
+            picked = _pick_args(rng, op, vals[i], vals, max_elems)
             if picked is None:
                 continue
             more, args = picked
@@ -314,7 +327,7 @@ def make_program(seed: int, n_ops: int = 12) -> Program:
                     out = np.asarray(_shadow(op, [vals[j] for j in ins], args), dtype=np.float32)
             except (FloatingPointError, ValueError, IndexError, ZeroDivisionError):
                 continue
-            if out.size == 0 or out.size > MAX_ELEMS or not np.all(np.isfinite(out)) or np.abs(out).max() > MAX_ABS:
+            if out.size == 0 or out.size > max_elems or not np.all(np.isfinite(out)) or np.abs(out).max() > MAX_ABS:
                 continue
             prog.ops.append((op, ins, args))
             vals.append(out)

@@ -10,6 +10,8 @@ accumulation orders agree, so what a third backend is compared on is arithmetic,
   digest_<seed>       sha1 of the program text (generator drift shows up as a digest mismatch, not as a numeric one)
   <seed>_loss / <seed>_v<i> / <seed>_g<i>   the REFERENCE's loss, terminal values and leaf gradients for the robust
                       programs with at most MAX_ELEMS_STORED result elements (first N_STORED of them)
+  robust_seeds_large / large_digest_<seed>   the same filter over the LARGE variant (fuzz_graphs.LARGE: extents up to
+                      1024, up to 4 M elements per node); seeds and program digests only
 """
 import hashlib
 import importlib.util
@@ -25,6 +27,7 @@ sys.path.insert(0, os.path.join(REPO, "tests"))
 sys.dont_write_bytecode = True
 
 N_SEEDS = 1200
+N_SEEDS_LARGE = 160
 N_STORED = 160
 MAX_ELEMS_STORED = 3000
 
@@ -66,9 +69,24 @@ def main():
             for i, g in enumerate(ref["grads"]):
                 out[f"{seed}_g{i}"] = np.asarray(g, dtype=np.float32)
     out["robust_seeds"] = np.array(robust, dtype=np.int64)
+    large = []
+    for seed in range(N_SEEDS_LARGE):          # the large variant: seeds only (the GPU test compares CUDA with the CPU path)
+        prog = F.make_program(seed, **F.LARGE)
+        ref = F.run_program(prog, ref_mod.Tensor, "cpu")
+        got = F.run_program(prog, Tensor, "cpu")
+        exact = F.run_program(prog, Tensor, "cpu", dtype=DType.FLOAT64)
+        try:
+            F.compare(ref, exact, 3e-6, "reference vs float64")
+            F.compare(got, exact, 3e-6, "package vs float64")
+            F.compare(got, ref, 2e-5, "package vs reference")
+        except AssertionError:
+            continue
+        large.append(seed)
+        out[f"large_digest_{seed}"] = np.array(digest(prog))
+    out["robust_seeds_large"] = np.array(large, dtype=np.int64)
     path = os.path.join(HERE, "fuzz_ref.npz")
     np.savez_compressed(path, **out)
-    print(f"{len(robust)} robust programs of {N_SEEDS}, {stored} with reference outputs -> {path} "
+    print(f"{len(robust)} robust programs of {N_SEEDS}, {stored} with reference outputs; {len(large)} large of {N_SEEDS_LARGE} -> {path} "
           f"({os.path.getsize(path) / 1024:.0f} KiB)")
 
 

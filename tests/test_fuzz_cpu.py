@@ -20,7 +20,7 @@ def fixture():
 
 
 def stored_seeds(fx):
-    return sorted(int(k.split("_")[1]) for k in fx.files if k.startswith("digest_"))
+    return sorted(int(k.split("_")[1]) for k in fx.files if k.startswith("digest_"))      # ("large_digest_*" do not match)
 
 
 def reference_result(fx, seed, prog):
@@ -36,6 +36,9 @@ def test_generator_reproduces_the_stored_programs():
     for seed in seeds:
         prog = F.make_program(seed)
         assert hashlib.sha1(prog.describe().encode()).hexdigest() == str(fx[f"digest_{seed}"]), f"program {seed} changed"
+    for seed in fx["robust_seeds_large"][:20]:
+        prog = F.make_program(int(seed), **F.LARGE)
+        assert hashlib.sha1(prog.describe().encode()).hexdigest() == str(fx[f"large_digest_{int(seed)}"]), f"large program {seed} changed"
     ops = {op for seed in fx["robust_seeds"][:400] for op, _, _ in F.make_program(int(seed)).ops}
     assert ops == set(F._NAMES), f"ops never generated: {set(F._NAMES) - ops}"
 

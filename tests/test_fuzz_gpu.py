@@ -48,3 +48,19 @@ def test_cuda_path_matches_cpu_path_on_robust_programs(Tensor):
         ref = F.run_program(prog, Tensor, "cpu")
         got = F.run_program(prog, Tensor, "cuda")
         F.compare(got, ref, TOL, f"seed {seed}\n{prog.describe()}")
+
+
+def test_cuda_path_matches_cpu_path_on_large_programs(Tensor):
+    """The large variant (extents 1 ... 1024 with odd ones in between, up to 4 M elements per node): the vectorised and
+    grid-stride elementwise paths, split reductions, strided copies of big views and - through matmul - the SIMT, mid-size
+    and persistent tensor-core engines, all inside one autograd graph.  1e-4 norm-wise where a program multiplies
+    matrices (the north_star's GEMM tolerance), 5e-5 otherwise."""
+    fx = np.load(os.path.join(GOLDEN, "fuzz_ref.npz"))
+    seeds = [int(s) for s in fx["robust_seeds_large"]]
+    assert len(seeds) >= 120
+    for seed in seeds:
+        prog = F.make_program(seed, **F.LARGE)
+        ref = F.run_program(prog, Tensor, "cpu")
+        got = F.run_program(prog, Tensor, "cuda")
+        tol = 1e-4 if any(op == "matmul" for op, _, _ in prog.ops) else TOL
+        F.compare(got, ref, tol, f"large seed {seed}\n{prog.describe()}")

@@ -276,12 +276,26 @@ __global__ void __launch_bounds__(CT) reduce_cols_flat_kernel(float* __restrict_
           else { acc.x += a[u].x; acc.y += a[u].y; acc.z += a[u].z; acc.w += a[u].w; }
         }
       }
-      for (; r < red; ++r) {
-        const float4 a = mtd::ld_stream4(px + r * inner);
-        if (HAS_W) {
-          const float4 b = mtd::ld_stream4(pw + r * sr);
-          acc.x += a.x * b.x; acc.y += a.y * b.y; acc.z += a.z * b.z; acc.w += a.w * b.w;
-        } else { acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w; }
+      if (r < red) {
+        // the last 1 - 3 rows (ALL the rows of a 2- or 3-way split-K fold): every load issued before the first addition -
+        // written as a loop the additions serialised the round trips (0.72 of HBM on a (2, 2^25) fold: 16 bytes in
+        // flight per thread)
+        const int left = (int)(red - r);
+        float4 a[3], b[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          if (u < left) {
+            a[u] = mtd::ld_stream4(px + (r + u) * inner);
+            if (HAS_W) b[u] = mtd::ld_stream4(pw + (r + u) * sr);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          if (u < left) {
+            if (HAS_W) { acc.x += a[u].x * b[u].x; acc.y += a[u].y * b[u].y; acc.z += a[u].z * b[u].z; acc.w += a[u].w * b[u].w; }
+            else { acc.x += a[u].x; acc.y += a[u].y; acc.z += a[u].z; acc.w += a[u].w; }
+          }
+        }
       }
       *reinterpret_cast<float4*>(out + o * inner + col) = acc;
     } else {
@@ -303,6 +317,18 @@ int ensure_tickets() {
   MT_CUDA(cudaMalloc((void**)&g_tickets, sizeof(unsigned int) * TICKETS));
   MT_CUDA(cudaMemset(g_tickets, 0, sizeof(unsigned int) * TICKETS));
   return MT_OK;
+}
+
+// resident CTAs per SM of one reduce_rows_kernel instantiation (asked once)
+template <bool HAS_W, bool VEC>
+int rows_resident() {
+  static int n = 0;
+  if (!n) {
+    int q = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, reduce_rows_kernel<HAS_W, VEC>, THREADS, 0) != cudaSuccess || q < 1) q = 4;
+    n = std::min(q, 8);
+  }
+  return n;
 }
 
 int reduce_rows(float* out, const float* x, long long outer, long long red, const float* w, long long so, long long sr) {
@@ -333,15 +359,21 @@ int reduce_rows(float* out, const float* x, long long outer, long long red, cons
     partial = scratch.f32();
     dst = partial;
   }
-  const int grid = (int)std::min<long long>(outer * splits, (long long)sms * 8);
   unsigned int* ticket = nullptr;
   if (splits > 1 && g_single_launch) {
     int rc = ensure_tickets();
     if (rc) return rc;
     ticket = g_tickets;
   }
-#define MT_ROWS(HW, VC) \
-  reduce_rows_kernel<HW, VC><<<grid, THREADS, 0, st>>>(dst, x, outer, red, splits, chunk, w, so, sr, out, ticket)
+  // ONE wave: the persistent grid is sized from the occupancy of the instantiation that runs.  A fixed 8 CTAs per SM was
+  // right at 31 registers; the ticket fold took the kernels to 34 / 38, 6 CTAs fit, and the 1184-CTA grid ran as a wave and
+  // a third - sum(axis=1) of 2^28 elements 192 us instead of 153 under ncu.  (Forcing 32 registers instead costs the
+  // long-loop sum(all) case 5 %.)
+#define MT_ROWS(HW, VC)                                                                                               \
+  do {                                                                                                                \
+    const int grid = (int)std::min<long long>(outer * splits, (long long)sms * rows_resident<HW, VC>());              \
+    reduce_rows_kernel<HW, VC><<<grid, THREADS, 0, st>>>(dst, x, outer, red, splits, chunk, w, so, sr, out, ticket);  \
+  } while (0)
   if (w) { if (vec) MT_ROWS(true, true); else MT_ROWS(true, false); }
   else { if (vec) MT_ROWS(false, true); else MT_ROWS(false, false); }
 #undef MT_ROWS

@@ -385,6 +385,17 @@ int reduce_rows(float* out, const float* x, long long outer, long long red, cons
   return MT_OK;
 }
 
+template <bool HAS_W, int V>
+int cols_resident() {
+  static int n = 0;
+  if (!n) {
+    int q = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, reduce_cols_kernel<HAS_W, V>, CT, 0) != cudaSuccess || q < 1) q = 4;
+    n = std::min(q, 8);
+  }
+  return n;
+}
+
 int reduce_cols(float* out, const float* x, long long outer, long long red, long long inner, const float* w,
                 long long so, long long sr, long long si, bool may_split = true) {
   cudaStream_t st = g().stream;
@@ -414,9 +425,12 @@ int reduce_cols(float* out, const float* x, long long outer, long long red, long
   const int TXr = 1 << tx_bits, TYr = CT >> tx_bits;
   const long long tiles = ceil_div(vcols, (long long)TXr);
   long long splits = 1;
-  if (may_split && tiles * oz < 4LL * sms) {
-    // fill the machine (4 CTAs per SM) but leave every row lane at least ~8 rows of work
-    splits = std::min<long long>(ceil_div(4LL * sms, tiles * oz), ceil_div(red, (long long)TYr * 8));
+  // CTAs of the instantiation that will run that fit on an SM (4 at 64 registers, 6 at 40): one full wave of them
+  const long long fill = (long long)sms * (w ? (vec ? cols_resident<true, 4>() : cols_resident<true, 1>())
+                                             : (vec ? cols_resident<false, 4>() : cols_resident<false, 1>()));
+  if (may_split && tiles * oz < fill) {
+    // fill the machine (one wave) but leave every row lane at least ~8 rows of work
+    splits = std::min<long long>(fill / (tiles * oz), ceil_div(red, (long long)TYr * 8));
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
   }

@@ -1,8 +1,8 @@
-"""Data-parallel host logic on CPU: world_size-2 gloo processes, Device.CPU replicas.
+"""Data-parallel host logic on CPU: world_size-2 and -4 gloo processes, Device.CPU replicas.
 
 Checks what the N>1 path adds on top of the single-GPU step - row sharding, the global-count
 loss scale, the per-parameter gradient hooks and exchange order, and that bias gradients are
-never exchanged - by comparing 2-rank post-SGD weights with a single-process full-batch step
+never exchanged - by comparing N-rank post-SGD weights with a single-process full-batch step
 and with the oracle."""
 import os
 import socket
@@ -49,11 +49,12 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_dp_matches_single_process_and_oracle(tmp_path):
+@pytest.mark.parametrize("world", [2, 4])
+def test_n_rank_dp_matches_single_process_and_oracle(tmp_path, world):
     import torch.multiprocessing as mp
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / f"rank{world - 1}.npz")
     from microtorch_b200 import workloads as W
     from oracle import workloads as OW
     wl = W.scaled(W.C5, 64, (32,) * 5)

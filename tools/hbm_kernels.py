@@ -94,11 +94,10 @@ def main():
             "sgd_multi_kernel": (lambda: K.sgd_multi([x], [y], 1e-9), 3 * B),
             "zero_multi_kernel": (lambda: K.zero_multi([out]), B),
         }
-        if True:
-            # tall-thin un-broadcast shapes (reduce_cols at 17-54 % with bank conflicts)
-            for rr, cc in ((n // 8, 8), (n // 32, 32), (n // 512, 512), (2, n // 2)):
-                tt = x.reshape((rr, cc))
-                work[f"reduce_cols tall-thin ({rr},{cc}) sum(axis=0)"] = (lambda tt=tt: K.sum(tt, 0), B + 4.0 * cc)
+        # tall-thin un-broadcast shapes (reduce_cols at 17-54 % with bank conflicts) and the short-fat one
+        for rr, cc in ((n // 8, 8), (n // 32, 32), (n // 512, 512), (2, n // 2)):
+            tt = x.reshape((rr, cc))
+            work[f"reduce_cols tall-thin ({rr},{cc}) sum(axis=0)"] = (lambda tt=tt: K.sum(tt, 0), B + 4.0 * cc)
         if n >= 65536 * 4096:
             # the 4096 -> 10 head of config #2 at 65536 rows: skinny forward / dX / dW (1 GiB operand streamed once)
             M, Kd, N = 65536, 4096, 10

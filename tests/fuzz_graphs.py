@@ -11,7 +11,8 @@ Used by tests/test_fuzz_cpu.py (package CPU path == live reference, fixtures == 
 (CUDA path == CPU path == reference fixtures).  The ops and argument forms follow the reference's signatures:
 overload.py:52-164 (+ - * / @ and their scalar / reflected forms, get_item), math.py (pow, log, exp, tanh, sqrt),
 reduce.py (sum with int / tuple axes, mean, max), base.py (view / reshape, transpose, squeeze, unsqueeze, broadcast_to),
-elementwise.py (abs, maximum, minimum).
+elementwise.py (abs, maximum, minimum) and - in the `select=True` variant - tensor.py:467-503 (comparisons with where,
+clip, threshold, masked_fill, sign).
 """
 from __future__ import annotations
 
@@ -76,6 +77,11 @@ def _shadow(op: str, xs: List[np.ndarray], args: Dict[str, Any]) -> np.ndarray:
     if op == "broadcast_to": return np.broadcast_to(a, args["shape"])
     if op == "getitem": return np.asarray(a[args["index"]])
     if op == "matmul": return np.asarray(a @ xs[1])
+    if op == "clip": return np.clip(a, np.float32(args["lo"]), np.float32(args["hi"]))
+    if op == "threshold": return np.where(a > np.float32(args["thr"]), a, np.float32(args["val"]))
+    if op == "where_gt": return np.where(a > np.float32(args["c"]), a, xs[1])
+    if op == "masked_fill": return np.where(xs[1] > np.float32(args["c"]), np.float32(args["val"]), a)
+    if op == "sign": return np.sign(a)
     raise KeyError(op)
 
 
@@ -114,6 +120,11 @@ def _apply(op: str, ts: list, args: Dict[str, Any], Tensor):
     if op == "broadcast_to": return a.broadcast_to(args["shape"])
     if op == "getitem": return a[args["index"]]
     if op == "matmul": return a @ ts[1]
+    if op == "clip": return a.clip(args["lo"], args["hi"])
+    if op == "threshold": return a.threshold(args["thr"], args["val"])
+    if op == "where_gt": return Tensor.where(a > args["c"], a, ts[1])
+    if op == "masked_fill": return a.masked_fill(ts[1] > args["c"], args["val"])
+    if op == "sign": return a.sign()
     raise KeyError(op)
 
 
@@ -126,6 +137,12 @@ _NAMES = [n for n, _ in _OPS]
 _WEIGHTS = np.array([w for _, w in _OPS], dtype=np.float64)
 _WEIGHTS /= _WEIGHTS.sum()
 _BINARY = ("add", "sub", "mul", "div", "maximum", "minimum")
+# the select family (tensor.py:467-503 of the reference: comparisons, where, clip, threshold, masked_fill, sign) - a separate
+# variant (`select=True`) so that the programs of the base variant, and their fixtures, do not change
+_SELECT_OPS = [("clip", 5), ("threshold", 4), ("where_gt", 5), ("masked_fill", 4), ("sign", 2)]
+_NAMES_SEL = _NAMES + [n for n, _ in _SELECT_OPS]
+_WEIGHTS_SEL = np.array([w for _, w in _OPS] + [w for _, w in _SELECT_OPS], dtype=np.float64)
+_WEIGHTS_SEL /= _WEIGHTS_SEL.sum()
 
 
 def _rand_shape(rng, dims) -> Tuple[int, ...]:
@@ -273,6 +290,33 @@ def _pick_args(rng, op: str, a: np.ndarray, vals: List[np.ndarray], max_elems: i
                 hi = int(rng.integers(lo + 1, d + 1))
                 idx.append(slice(lo, hi, int(rng.choice([1, 1, 2]))))
         return (), {"index": tuple(idx) if len(idx) > 1 or rng.random() < 0.5 else idx[0]}
+    if op in ("clip", "threshold", "where_gt", "masked_fill", "sign"):
+        if a.size == 0:
+            return None
+
+        def clear_of(x, c):                   # no element within reach of the comparison's flip
+            return np.abs(x - np.float32(c)).min(initial=1.0) > 1e-4 * (1.0 + abs(c))
+
+        lo_v, hi_v = float(a.min()), float(a.max())
+        if op == "sign":
+            return ((), {}) if clear_of(a, 0.0) else None
+        if op == "clip":
+            lo = float(np.round(rng.uniform(lo_v - 0.2, 0.5 * (lo_v + hi_v)), 3))
+            hi = float(np.round(rng.uniform(0.5 * (lo_v + hi_v), hi_v + 0.2), 3))
+            return ((), {"lo": lo, "hi": hi}) if lo < hi and clear_of(a, lo) and clear_of(a, hi) else None
+        if op == "threshold":
+            thr = float(np.round(rng.uniform(lo_v - 0.1, hi_v + 0.1), 3))
+            return ((), {"thr": thr, "val": float(np.round(rng.uniform(-1.0, 1.0), 3))}) if clear_of(a, thr) else None
+        cands = [j for j, b in enumerate(vals) if b.shape == a.shape]      # where() does not un-broadcast its gradients
+        if not cands:
+            return None
+        j = int(rng.choice(cands))
+        if op == "where_gt":
+            c = float(np.round(rng.uniform(lo_v, hi_v), 3))
+            return ((j,), {"c": c}) if clear_of(a, c) else None
+        b = vals[j]
+        c = float(np.round(rng.uniform(float(b.min()), float(b.max())), 3))
+        return ((j,), {"c": c, "val": float(np.round(rng.uniform(-1.0, 1.0), 3))}) if clear_of(b, c) else None
     if op == "matmul":
         if nd == 0 or nd > 2:
             return None
@@ -293,7 +337,8 @@ LARGE_MAX_ELEMS = 1 << 22
 LARGE = dict(dims=LARGE_DIMS, max_elems=LARGE_MAX_ELEMS, min_base=1 << 16)
 
 
-def make_program(seed: int, n_ops: int = 12, dims=DIMS, max_elems: int = MAX_ELEMS, min_base: int = 0) -> Program:
+def make_program(seed: int, n_ops: int = 12, dims=DIMS, max_elems: int = MAX_ELEMS, min_base: int = 0,
+                 select: bool = False) -> Program:
     """`**LARGE` gives the programs of the large variant: odd extents next to powers
     of two, up to 4 M elements per node - the vectorised / grid-stride / split-reduction paths and, through matmul, the
     tensor-core engines."""
@@ -312,9 +357,10 @@ def make_program(seed: int, n_ops: int = 12, dims=DIMS, max_elems: int = MAX_ELE
         prog.leaves.append(arr)
         vals.append(arr)
     used = set()
+    grad = [True] * len(vals)                 # does the node require a gradient?  (sign() of anything does not)
     for _ in range(n_ops):
         for _attempt in range(30):
-            op = _NAMES[int(rng.choice(len(_NAMES), p=_WEIGHTS))]
+            op = _NAMES_SEL[int(rng.choice(len(_NAMES_SEL), p=_WEIGHTS_SEL))] if select else _NAMES[int(rng.choice(len(_NAMES), p=_WEIGHTS))]
             recent = rng.random() < 0.6
             i = int(rng.integers(max(0, len(vals) - 3), len(vals))) if recent else int(rng.integers(0, len(vals)))
             picked = _pick_args(rng, op, vals[i], vals, max_elems)
@@ -331,10 +377,11 @@ def make_program(seed: int, n_ops: int = 12, dims=DIMS, max_elems: int = MAX_ELE
                 continue
             prog.ops.append((op, ins, args))
             vals.append(out)
+            grad.append(op != "sign" and any(grad[j] for j in (ins[:1] if op == "masked_fill" else ins)))
             used.update(ins)
             break
     n = len(vals)
-    loose = [k for k in range(len(prog.leaves), n) if k not in used] or [n - 1]
+    loose = [k for k in range(len(prog.leaves), n) if k not in used and grad[k]] or [max(k for k in range(n) if grad[k])]
     for k in loose[-3:]:
         w = rng.uniform(0.5, 1.5, size=vals[k].shape).astype(np.float32)
         prog.terminals.append((k, w))

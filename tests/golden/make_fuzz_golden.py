@@ -12,6 +12,7 @@ accumulation orders agree, so what a third backend is compared on is arithmetic,
                       programs with at most MAX_ELEMS_STORED result elements (first N_STORED of them)
   robust_seeds_large / large_digest_<seed>   the same filter over the LARGE variant (fuzz_graphs.LARGE: extents up to
                       1024, up to 4 M elements per node); seeds and program digests only
+  robust_seeds_select / select_digest_<seed>  the same for the select-family variant (make_program(select=True))
 """
 import hashlib
 import importlib.util
@@ -28,6 +29,7 @@ sys.dont_write_bytecode = True
 
 N_SEEDS = 1200
 N_SEEDS_LARGE = 160
+N_SEEDS_SELECT = 500
 N_STORED = 160
 MAX_ELEMS_STORED = 3000
 
@@ -84,9 +86,25 @@ def main():
         large.append(seed)
         out[f"large_digest_{seed}"] = np.array(digest(prog))
     out["robust_seeds_large"] = np.array(large, dtype=np.int64)
+    sel = []
+    for seed in range(N_SEEDS_SELECT):         # the select-family variant (clip / threshold / where / masked_fill / sign): seeds only
+        prog = F.make_program(seed, select=True)
+        ref = F.run_program(prog, ref_mod.Tensor, "cpu")
+        got = F.run_program(prog, Tensor, "cpu")
+        exact = F.run_program(prog, Tensor, "cpu", dtype=DType.FLOAT64)
+        try:
+            F.compare(ref, exact, 3e-6, "reference vs float64")
+            F.compare(got, exact, 3e-6, "package vs float64")
+            F.compare(got, ref, 2e-5, "package vs reference")
+        except AssertionError:
+            continue
+        sel.append(seed)
+        if len(sel) <= 20:
+            out[f"select_digest_{seed}"] = np.array(digest(prog))
+    out["robust_seeds_select"] = np.array(sel, dtype=np.int64)
     path = os.path.join(HERE, "fuzz_ref.npz")
     np.savez_compressed(path, **out)
-    print(f"{len(robust)} robust programs of {N_SEEDS}, {stored} with reference outputs; {len(large)} large of {N_SEEDS_LARGE} -> {path} "
+    print(f"{len(robust)} robust programs of {N_SEEDS}, {stored} with reference outputs; {len(large)} large of {N_SEEDS_LARGE}, {len(sel)} select of {N_SEEDS_SELECT} -> {path} "
           f"({os.path.getsize(path) / 1024:.0f} KiB)")
 
 

@@ -20,7 +20,7 @@ def fixture():
 
 
 def stored_seeds(fx):
-    return sorted(int(k.split("_")[1]) for k in fx.files if k.startswith("digest_"))      # ("large_digest_*" do not match)
+    return sorted(int(k.split("_")[1]) for k in fx.files if k.startswith("digest_"))      # ("large_" / "select_digest_*" do not match)
 
 
 def reference_result(fx, seed, prog):
@@ -39,6 +39,12 @@ def test_generator_reproduces_the_stored_programs():
     for seed in fx["robust_seeds_large"][:20]:
         prog = F.make_program(int(seed), **F.LARGE)
         assert hashlib.sha1(prog.describe().encode()).hexdigest() == str(fx[f"large_digest_{int(seed)}"]), f"large program {seed} changed"
+    for key in [k for k in fx.files if k.startswith("select_digest_")]:
+        seed = int(key.split("_")[2])
+        prog = F.make_program(seed, select=True)
+        assert hashlib.sha1(prog.describe().encode()).hexdigest() == str(fx[key]), f"select program {seed} changed"
+    sel_ops = {op for seed in fx["robust_seeds_select"][:300] for op, _, _ in F.make_program(int(seed), select=True).ops}
+    assert {n for n, _ in F._SELECT_OPS} <= sel_ops
     ops = {op for seed in fx["robust_seeds"][:400] for op, _, _ in F.make_program(int(seed)).ops}
     assert ops == set(F._NAMES), f"ops never generated: {set(F._NAMES) - ops}"
 
@@ -72,3 +78,14 @@ def test_cpu_path_matches_live_reference_on_fresh_programs():
         F.compare(got, ref, 2e-5, f"seed {seed}\n{prog.describe()}")
         compared += 1
     assert compared >= 1400, compared
+    compared = 0
+    for seed in range(100000, 101000):                          # the select-family variant
+        prog = F.make_program(seed, select=True)
+        ref = F.run_program(prog, ref_mod.Tensor, "cpu")
+        got = F.run_program(prog, Tensor, "cpu")
+        if not (F.well_conditioned(prog, Tensor, ref, 3e-6, DType.FLOAT64)
+                and F.well_conditioned(prog, Tensor, got, 3e-6, DType.FLOAT64)):
+            continue
+        F.compare(got, ref, 2e-5, f"select seed {seed}\n{prog.describe()}")
+        compared += 1
+    assert compared >= 930, compared

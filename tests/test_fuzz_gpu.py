@@ -64,3 +64,18 @@ def test_cuda_path_matches_cpu_path_on_large_programs(Tensor):
         got = F.run_program(prog, Tensor, "cuda")
         tol = 1e-4 if any(op == "matmul" for op, _, _ in prog.ops) else TOL
         F.compare(got, ref, tol, f"large seed {seed}\n{prog.describe()}")
+
+
+def test_cuda_path_matches_cpu_path_on_select_family_programs(Tensor):
+    """The select-family variant: comparisons feeding where / clip / threshold / masked_fill / sign (reference
+    tensor.py:467-503 - on CuPy the reference builds those masks and constants on the CPU, Q8, so this family never ran on
+    its CUDA path; here it runs on the device) mixed into the same random graphs.  The generator keeps every compared
+    element 1e-4 clear of its threshold, so which branch wins does not hang on an ulp."""
+    fx = np.load(os.path.join(GOLDEN, "fuzz_ref.npz"))
+    seeds = [int(s) for s in fx["robust_seeds_select"][:400]]
+    assert len(seeds) >= 350
+    for seed in seeds:
+        prog = F.make_program(seed, select=True)
+        ref = F.run_program(prog, Tensor, "cpu")
+        got = F.run_program(prog, Tensor, "cuda")
+        F.compare(got, ref, TOL, f"select seed {seed}\n{prog.describe()}")
